@@ -1,0 +1,43 @@
+# Builds, in-tree:
+#   navierstokes-capoferri_cecchettini_untila_b200/libnsb_host.so  host setup library (C++17, no CUDA)
+#   navierstokes-capoferri_cecchettini_untila_b200/libnsb.so       sm_100a kernels + hot-path C ABI
+#   navierstokes-capoferri_cecchettini_untila_b200/drivers/*       reference-style driver mains (C++)
+#   oracle/libns_oracle.so                                          CPU oracle (test infrastructure)
+PKG      := navierstokes-capoferri_cecchettini_untila_b200
+CXX      := /usr/bin/g++
+NVCC     ?= /usr/local/cuda/bin/nvcc
+CXXFLAGS := -O3 -march=x86-64-v3 -std=c++17 -fPIC -fopenmp -Wall -Wextra -Wno-unused-parameter
+NVFLAGS  := -ccbin /usr/bin/g++ -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
+            -Xcompiler -fPIC,-fopenmp,-Wall -Xptxas -v --use_fast_math=false
+
+HOST_SRC := $(PKG)/host/mesh.cpp $(PKG)/host/fespace.cpp $(PKG)/host/nsb_host_capi.cpp
+HOST_HDR := $(wildcard $(PKG)/host/*.hpp) include/nsb_host.h
+CU_SRC   := $(PKG)/csrc/nsb_capi.cu
+CU_HDR   := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/nsb.h
+
+all: host oracle cuda drivers
+
+host: $(PKG)/libnsb_host.so
+oracle: oracle/libns_oracle.so
+cuda: $(PKG)/libnsb.so
+
+$(PKG)/libnsb_host.so: $(HOST_SRC) $(HOST_HDR)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRC)
+
+oracle/libns_oracle.so: oracle/ns_oracle.cpp oracle/ns_oracle.h
+	$(CXX) $(CXXFLAGS) -shared -o $@ oracle/ns_oracle.cpp
+
+$(PKG)/libnsb.so: $(CU_SRC) $(CU_HDR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRC) -cudart static -ldl 2> $(PKG)/csrc/ptxas.log || (cat $(PKG)/csrc/ptxas.log; false)
+
+DRIVER_SRC := $(wildcard $(PKG)/drivers/*.cpp)
+DRIVER_BIN := $(DRIVER_SRC:.cpp=)
+drivers: $(DRIVER_BIN)
+$(PKG)/drivers/%: $(PKG)/drivers/%.cpp $(PKG)/host/NavierStokes.cpp $(PKG)/host/NavierStokes.hpp $(PKG)/libnsb_host.so $(PKG)/libnsb.so
+	$(CXX) $(CXXFLAGS) -I$(PKG)/host -Iinclude -o $@ $< $(PKG)/host/NavierStokes.cpp \
+	    -L$(PKG) -lnsb_host -lnsb -Wl,-rpath,'$$ORIGIN/..'
+
+clean:
+	rm -f $(PKG)/*.so oracle/*.so $(DRIVER_BIN) $(PKG)/csrc/ptxas.log
+
+.PHONY: all host oracle cuda drivers clean

@@ -1,0 +1,138 @@
+/* nsb: C ABI of the B200 (sm_100a) hot path -- per-time-step assembly of the
+ * semi-implicit Oseen system on Taylor-Hood P2/P1 simplices, the aSIMPLE-
+ * preconditioned GMRES solve, and the Cd/Cl force integrals.
+ *
+ * This is the boundary a NavierStokes-style host class binds to (SURVEY.md
+ * §8b).  Plain pointers and sizes only; every function returns 0 on success or
+ * a negative NSB_E* code and never throws; nsb_last_error(ctx) explains.  Host
+ * pointers are not retained after a call returns.  There is no CPU fallback:
+ * nsb_create fails when no CUDA device is usable.
+ *
+ * Reference interface each entry point replaces (file:line in
+ * /root/reference/src):
+ *   nsb_set_mesh / nsb_set_dofs / nsb_set_pattern   NavierStokes::setup            NavierStokes.cpp:4-131
+ *   nsb_set_quadrature                              QGaussSimplex(fe->degree+1)    NavierStokes.cpp:50,54
+ *   nsb_set_params                                  ctor deltat, set_re_number nu  NavierStokes.hpp:173-189, .cpp:332-341
+ *   nsb_set_solution / nsb_get_solution             solution_owned / solution      NavierStokes.hpp:251-252, .cpp:395,465
+ *   nsb_set_dirichlet                               interpolate_boundary_values    NavierStokes.cpp:297-324
+ *   nsb_assemble                                    NavierStokes::assemble         NavierStokes.cpp:133-330
+ *   nsb_solve_time_step                             NavierStokes::solve_time_step  NavierStokes.cpp:344-397
+ *                                                   + PreconditionASIMPLE          NavierStokes.cpp:934-995
+ *   nsb_set_force_faces / nsb_compute_forces        NavierStokes::compute_forces   NavierStokes.cpp:831-929
+ *   nsb_get_matrix_values / nsb_get_rhs / nsb_vmult parity taps on system_matrix / system_rhs (NavierStokes.hpp:248-250)
+ */
+#ifndef NSB_H
+#define NSB_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nsb_ctx nsb_ctx;
+
+enum {
+  NSB_OK = 0,
+  NSB_ECUDA = -1,     /* CUDA runtime error / no device */
+  NSB_EARG = -2,      /* bad argument or call order */
+  NSB_ESTRUCT = -3,   /* dofs/pattern do not have the Taylor-Hood structure */
+  NSB_ENOCONV = -4,   /* GMRES hit max_it (deal.II: SolverControl::NoConvergence) */
+  NSB_ENCCL = -5      /* NCCL error */
+};
+
+/* blocks of the 2x2 system matrix (A11 is empty) and the Schur approximation */
+enum { NSB_A00 = 0, NSB_A01 = 1, NSB_A10 = 2, NSB_S = 3 };
+/* quadrature tables: deal.II 9.3.x (2D 7-pt hard-coded order, 3D 10-pt degree 3)
+ * or >= 9.4 (Witherden-Vincent: 2D 7-pt, 3D 14-pt degree 5) */
+enum { NSB_QUAD_DEALII93 = 0, NSB_QUAD_DEALII95 = 1 };
+/* treatment of the diagonal of constrained rows in apply_boundary_values */
+enum { NSB_BCDIAG_KEEP = 0, NSB_BCDIAG_FIRST = 1 };
+/* preconditioner selection (reference NavierStokes.cpp:352-373) */
+enum { NSB_PREC_ASIMPLE = 0, NSB_PREC_IDENTITY = 1 };
+
+const char *nsb_last_error(const nsb_ctx *ctx);
+/* Number of CUDA devices visible (0 when none / no driver). */
+int nsb_device_count(void);
+
+int nsb_create(int dim, int device_id, nsb_ctx **out);
+void nsb_destroy(nsb_ctx *ctx);
+
+/* ---- immutable inputs (once) ------------------------------------------ */
+int nsb_set_mesh(nsb_ctx *ctx, int64_t n_verts, const double *xyz, int64_t n_cells, const uint32_t *cell_verts);
+/* cell_dofs: n_cells x dofs_per_cell in deal.II FESystem cell order
+ * (per vertex u_0..u_{dim-1}, p; then per line u_0..u_{dim-1}); velocity dofs
+ * must be dim*node+c and pressure dofs n_u+vertex. */
+int nsb_set_dofs(nsb_ctx *ctx, uint32_t n_u, uint32_t n_p, const uint32_t *cell_dofs);
+/* Canonical CSR of a block (rows ascending, columns ascending, block-local
+ * column indices).  Blocks A00, A01, A10 are required; NSB_S is optional (the
+ * structural product A10*A01 is formed on the device when absent). */
+int nsb_set_pattern(nsb_ctx *ctx, int block, int64_t n_rows, const int64_t *rowptr, const uint32_t *colind);
+/* Alternative to nsb_set_pattern(NSB_A00): node-level adjacency, expanded on
+ * the device to the canonical A00 = nodes (x) ones(dim,dim) pattern. */
+int nsb_set_node_pattern(nsb_ctx *ctx, int64_t n_nodes, const int64_t *rowptr, const uint32_t *colind);
+int nsb_set_quadrature(nsb_ctx *ctx, int rule_id);
+/* Finishes setup: scatter maps, diagonal positions, work vectors. Called
+ * implicitly by the first nsb_assemble. */
+int nsb_finalize_setup(nsb_ctx *ctx);
+
+/* ---- parameters ------------------------------------------------------- */
+int nsb_set_params(nsb_ctx *ctx, double deltat, double nu);
+int nsb_set_bc_diag_mode(nsb_ctx *ctx, int mode);
+/* Outer GMRES: stop when the preconditioned residual <= rtol*||rhs||_2
+ * (reference :348), restart length (deal.II default 28), max iterations
+ * (10000).  alpha: aSIMPLE relaxation (NavierStokes.hpp:306, 0.5). */
+int nsb_set_solver(nsb_ctx *ctx, double gmres_rtol, int restart, int max_it, double alpha, int preconditioner);
+/* Inner solves of aSIMPLE: fixed-degree Chebyshev-Jacobi polynomials in place
+ * of the reference's ILU-preconditioned GMRES to 1e-2 (north star: Jacobi-type
+ * inner sweeps).  sweeps = polynomial degree; eig_ratio = assumed
+ * lambda_max/lambda_min of D^-1 M targeted by the polynomial. */
+int nsb_set_inner(nsb_ctx *ctx, int sweeps_F, double eig_ratio_F, int sweeps_S, double eig_ratio_S);
+
+/* ---- state ------------------------------------------------------------ */
+int nsb_set_solution(nsb_ctx *ctx, const double *x_host);   /* n_u+n_p, host -> device */
+int nsb_get_solution(nsb_ctx *ctx, double *x_host);         /* device -> host */
+int nsb_set_dirichlet(nsb_ctx *ctx, int64_t n_bc, const uint32_t *dofs, const double *values);
+/* Values only (same dof list), scaled by `factor` on the device: the
+ * time-dependent inlets g(x,t) = g(x) * sin(pi t/8) of the *_03 drivers. */
+int nsb_scale_dirichlet(nsb_ctx *ctx, double factor);
+int nsb_set_force_faces(nsb_ctx *ctx, int64_t n_faces, const uint32_t *cell, const double *normal,
+                        const double *measure);
+
+/* ---- the per-time-step path ------------------------------------------- */
+int nsb_assemble(nsb_ctx *ctx, double time);
+int nsb_solve_time_step(nsb_ctx *ctx, int *iters, double *t_prec, double *t_solve);
+/* out = {drag, lift, cd, cl}; u_mean = InletVelocity::get_mean_vel(). */
+int nsb_compute_forces(nsb_ctx *ctx, double u_mean, double out[4]);
+
+/* ---- parity taps / bench hooks ---------------------------------------- */
+int nsb_get_matrix_values(nsb_ctx *ctx, int block, double *vals_host);
+int nsb_get_pattern(nsb_ctx *ctx, int block, int64_t *rowptr_host, uint32_t *colind_host);
+int64_t nsb_nnz(const nsb_ctx *ctx, int block);
+int nsb_get_rhs(nsb_ctx *ctx, double *rhs_host);
+/* y = A x with host vectors (n_u+n_p). */
+int nsb_vmult(nsb_ctx *ctx, const double *x_host, double *y_host);
+/* Device-resident micro-benchmarks: run `reps` launches and return the mean
+ * kernel time in milliseconds measured with CUDA events on the ctx stream.
+ * which: 0 block SpMV y=Ax (canonical CSR), 1 assembly (zero+cell loop+BC),
+ * 2 preconditioner apply, 3 S = B Di Bt, 4 Chebyshev sweep on F. */
+int nsb_bench_kernel(nsb_ctx *ctx, int which, int reps, double *ms_mean);
+/* Launch counter of this context's own kernels (for bench.py gpu_launches). */
+int64_t nsb_launch_count(const nsb_ctx *ctx);
+/* timers of the last step in ms: [0] assemble, [1] prec init, [2] solve, [3] forces */
+int nsb_timers(const nsb_ctx *ctx, double out_ms[4]);
+/* info: [0] n_u [1] n_p [2] n_cells [3] nnz A00 [4] nnz A01 [5] nnz A10 [6] nnz S
+ *       [7] n_q [8] device bytes allocated */
+int nsb_info(const nsb_ctx *ctx, int64_t out[9]);
+
+/* pinned host memory for callers that want asynchronous copies */
+void *nsb_alloc_pinned(int64_t bytes);
+void nsb_free_pinned(void *p);
+
+/* ---- multi-GPU (one process per GPU) ---------------------------------- */
+/* 128-byte NCCL unique id created on rank 0 and broadcast by the caller. */
+int nsb_comm_unique_id(char id[128]);
+int nsb_comm_init(nsb_ctx *ctx, int rank, int n_ranks, const char id[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,229 @@
+"""ctypes binding of include/nsb.h (libnsb.so, the sm_100a hot path)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+A00, A01, A10, S = 0, 1, 2, 3
+QUAD_DEALII93, QUAD_DEALII95 = 0, 1
+PREC_ASIMPLE, PREC_IDENTITY = 0, 1
+
+# every symbol include/nsb.h declares (tests check the .so exports them all)
+SYMBOLS = [
+    "nsb_last_error", "nsb_device_count", "nsb_create", "nsb_destroy", "nsb_set_mesh", "nsb_set_dofs",
+    "nsb_set_pattern", "nsb_set_node_pattern", "nsb_set_quadrature", "nsb_finalize_setup", "nsb_set_params",
+    "nsb_set_bc_diag_mode", "nsb_set_solver", "nsb_set_inner", "nsb_set_solution", "nsb_get_solution",
+    "nsb_set_dirichlet", "nsb_scale_dirichlet", "nsb_set_force_faces", "nsb_assemble", "nsb_solve_time_step",
+    "nsb_compute_forces", "nsb_get_matrix_values", "nsb_get_pattern", "nsb_nnz", "nsb_get_rhs", "nsb_vmult",
+    "nsb_bench_kernel", "nsb_launch_count", "nsb_timers", "nsb_info", "nsb_alloc_pinned", "nsb_free_pinned",
+    "nsb_comm_unique_id", "nsb_comm_init",
+]
+
+
+class DeviceError(RuntimeError):
+    pass
+
+
+def device_lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "libnsb.so")
+        if not os.path.exists(path):
+            raise DeviceError("libnsb.so is not built (run `make cuda`); there is no CPU fallback")
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        p = C.c_void_p
+        f64p, u32p, i64p = (C.POINTER(t) for t in (C.c_double, C.c_uint32, C.c_int64))
+        L.nsb_last_error.argtypes = [p]
+        L.nsb_last_error.restype = C.c_char_p
+        L.nsb_create.argtypes = [C.c_int, C.c_int, C.POINTER(p)]
+        L.nsb_destroy.argtypes = [p]
+        L.nsb_set_mesh.argtypes = [p, C.c_int64, f64p, C.c_int64, u32p]
+        L.nsb_set_dofs.argtypes = [p, C.c_uint32, C.c_uint32, u32p]
+        L.nsb_set_pattern.argtypes = [p, C.c_int, C.c_int64, i64p, u32p]
+        L.nsb_set_node_pattern.argtypes = [p, C.c_int64, i64p, u32p]
+        L.nsb_set_quadrature.argtypes = [p, C.c_int]
+        L.nsb_finalize_setup.argtypes = [p]
+        L.nsb_set_params.argtypes = [p, C.c_double, C.c_double]
+        L.nsb_set_bc_diag_mode.argtypes = [p, C.c_int]
+        L.nsb_set_solver.argtypes = [p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int]
+        L.nsb_set_inner.argtypes = [p, C.c_int, C.c_double, C.c_int, C.c_double]
+        L.nsb_set_solution.argtypes = [p, f64p]
+        L.nsb_get_solution.argtypes = [p, f64p]
+        L.nsb_set_dirichlet.argtypes = [p, C.c_int64, u32p, f64p]
+        L.nsb_scale_dirichlet.argtypes = [p, C.c_double]
+        L.nsb_set_force_faces.argtypes = [p, C.c_int64, u32p, f64p, f64p]
+        L.nsb_assemble.argtypes = [p, C.c_double]
+        L.nsb_solve_time_step.argtypes = [p, C.POINTER(C.c_int), f64p, f64p]
+        L.nsb_compute_forces.argtypes = [p, C.c_double, f64p]
+        L.nsb_get_matrix_values.argtypes = [p, C.c_int, f64p]
+        L.nsb_get_pattern.argtypes = [p, C.c_int, i64p, u32p]
+        L.nsb_nnz.argtypes = [p, C.c_int]
+        L.nsb_nnz.restype = C.c_int64
+        L.nsb_get_rhs.argtypes = [p, f64p]
+        L.nsb_vmult.argtypes = [p, f64p, f64p]
+        L.nsb_bench_kernel.argtypes = [p, C.c_int, C.c_int, f64p]
+        L.nsb_launch_count.argtypes = [p]
+        L.nsb_launch_count.restype = C.c_int64
+        L.nsb_timers.argtypes = [p, f64p]
+        L.nsb_info.argtypes = [p, i64p]
+        L.nsb_alloc_pinned.argtypes = [C.c_int64]
+        L.nsb_alloc_pinned.restype = C.c_void_p
+        L.nsb_free_pinned.argtypes = [C.c_void_p]
+        L.nsb_comm_unique_id.argtypes = [C.c_char_p]
+        L.nsb_comm_init.argtypes = [p, C.c_int, C.c_int, C.c_char_p]
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Device:
+    """One ``nsb_ctx``: the device-resident system of one NavierStokes problem."""
+
+    def __init__(self, dim: int, device_id: int = 0):
+        self.L = device_lib()
+        self.dim = dim
+        h = C.c_void_p()
+        rc = self.L.nsb_create(dim, device_id, C.byref(h))
+        if rc != 0:
+            raise DeviceError(f"nsb_create failed ({rc}): no usable CUDA device; there is no CPU fallback")
+        self.h = h
+        self.N = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise DeviceError(f"nsb error {rc}: {self.L.nsb_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nsb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setup ---------------------------------------------------------
+    def load_problem(self, prob, quad_rule=QUAD_DEALII95, node_pattern=False):
+        """Uploads mesh, dofs, patterns, Dirichlet list and obstacle faces of a
+        host :class:`Problem` (already built)."""
+        s = prob.sizes()
+        xyz, cells = prob.array("xyz"), prob.array("cells")
+        self._chk(self.L.nsb_set_mesh(self.h, s["n_verts"], _p(xyz, C.c_double), s["n_cells"], _p(cells, C.c_uint32)))
+        cd = prob.array("cell_dofs")
+        self._chk(self.L.nsb_set_dofs(self.h, s["n_u"], s["n_p"], _p(cd, C.c_uint32)))
+        for blk, name in ((A00, "a00"), (A01, "a01"), (A10, "a10"), (S, "s")):
+            if blk == A00 and node_pattern:
+                rp, ci = prob.array("nodes.rowptr"), prob.array("nodes.colind")
+                self._chk(self.L.nsb_set_node_pattern(self.h, rp.size - 1, _p(rp, C.c_int64), _p(ci, C.c_uint32)))
+                continue
+            rp, ci = prob.array(name + ".rowptr"), prob.array(name + ".colind")
+            self._chk(self.L.nsb_set_pattern(self.h, blk, rp.size - 1, _p(rp, C.c_int64), _p(ci, C.c_uint32)))
+        self._chk(self.L.nsb_set_quadrature(self.h, quad_rule))
+        self.set_dirichlet(prob.array("bc.dofs"), prob.array("bc.values"))
+        fc, fn, fm = prob.array("ff.cell"), prob.array("ff.normal"), prob.array("ff.measure")
+        self._chk(self.L.nsb_set_force_faces(self.h, fc.size, _p(fc, C.c_uint32), _p(fn, C.c_double),
+                                             _p(fm, C.c_double)))
+        self._chk(self.L.nsb_finalize_setup(self.h))
+        self.N = s["n_u"] + s["n_p"]
+        self.n_u, self.n_p = s["n_u"], s["n_p"]
+        return self
+
+    def set_params(self, deltat, nu):
+        self._chk(self.L.nsb_set_params(self.h, deltat, nu))
+
+    def set_bc_diag_mode(self, mode):
+        self._chk(self.L.nsb_set_bc_diag_mode(self.h, mode))
+
+    def set_solver(self, gmres_rtol=1e-6, restart=28, max_it=10000, alpha=0.5, preconditioner=PREC_ASIMPLE):
+        self._chk(self.L.nsb_set_solver(self.h, gmres_rtol, restart, max_it, alpha, preconditioner))
+
+    def set_inner(self, sweeps_F, eig_ratio_F, sweeps_S, eig_ratio_S):
+        self._chk(self.L.nsb_set_inner(self.h, sweeps_F, eig_ratio_F, sweeps_S, eig_ratio_S))
+
+    def set_dirichlet(self, dofs, values):
+        dofs = np.ascontiguousarray(dofs, np.uint32)
+        values = np.ascontiguousarray(values, np.float64)
+        self._chk(self.L.nsb_set_dirichlet(self.h, dofs.size, _p(dofs, C.c_uint32), _p(values, C.c_double)))
+
+    def scale_dirichlet(self, factor):
+        self._chk(self.L.nsb_scale_dirichlet(self.h, factor))
+
+    # ---- state -----------------------------------------------------------
+    def set_solution(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        assert x.size == self.N
+        self._chk(self.L.nsb_set_solution(self.h, _p(x, C.c_double)))
+
+    def solution(self, out=None):
+        out = np.empty(self.N, np.float64) if out is None else out
+        self._chk(self.L.nsb_get_solution(self.h, _p(out, C.c_double)))
+        return out
+
+    # ---- hot path -----------------------------------------------------------
+    def assemble(self, time):
+        self._chk(self.L.nsb_assemble(self.h, time))
+
+    def solve_time_step(self):
+        it, tp, ts = C.c_int(), C.c_double(), C.c_double()
+        self._chk(self.L.nsb_solve_time_step(self.h, C.byref(it), C.byref(tp), C.byref(ts)))
+        return it.value, tp.value, ts.value
+
+    def compute_forces(self, u_mean):
+        out = np.empty(4, np.float64)
+        self._chk(self.L.nsb_compute_forces(self.h, u_mean, _p(out, C.c_double)))
+        return out
+
+    # ---- taps -----------------------------------------------------------------
+    def nnz(self, block):
+        return int(self.L.nsb_nnz(self.h, block))
+
+    def values(self, block):
+        out = np.empty(self.nnz(block), np.float64)
+        self._chk(self.L.nsb_get_matrix_values(self.h, block, _p(out, C.c_double)))
+        return out
+
+    def pattern(self, block):
+        n_rows = self.n_p if block in (A10, S) else self.n_u
+        rp, ci = np.empty(n_rows + 1, np.int64), np.empty(self.nnz(block), np.uint32)
+        self._chk(self.L.nsb_get_pattern(self.h, block, _p(rp, C.c_int64), _p(ci, C.c_uint32)))
+        return rp, ci
+
+    def rhs(self):
+        out = np.empty(self.N, np.float64)
+        self._chk(self.L.nsb_get_rhs(self.h, _p(out, C.c_double)))
+        return out
+
+    def vmult(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.empty(self.N, np.float64)
+        self._chk(self.L.nsb_vmult(self.h, _p(x, C.c_double), _p(y, C.c_double)))
+        return y
+
+    def bench_kernel(self, which, reps):
+        ms = C.c_double()
+        self._chk(self.L.nsb_bench_kernel(self.h, which, reps, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.L.nsb_launch_count(self.h))
+
+    def timers(self):
+        out = np.empty(4, np.float64)
+        self._chk(self.L.nsb_timers(self.h, _p(out, C.c_double)))
+        return out
+
+    def info(self):
+        out = (C.c_int64 * 9)()
+        self._chk(self.L.nsb_info(self.h, out))
+        keys = ["n_u", "n_p", "n_cells", "nnz_a00", "nnz_a01", "nnz_a10", "nnz_s", "n_q", "device_bytes"]
+        return dict(zip(keys, [int(v) for v in out]))
