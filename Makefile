@@ -8,7 +8,7 @@ CXX      := /usr/bin/g++
 NVCC     ?= /usr/local/cuda/bin/nvcc
 CXXFLAGS := -O3 -march=x86-64-v3 -std=c++17 -fPIC -fopenmp -Wall -Wextra -Wno-unused-parameter
 NVFLAGS  := -ccbin /usr/bin/g++ -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
-            -Xcompiler -fPIC,-fopenmp,-Wall -Xptxas -v --use_fast_math=false
+            -Xcompiler -fPIC,-fopenmp,-Wall -Xptxas -v
 
 HOST_SRC := $(PKG)/host/mesh.cpp $(PKG)/host/fespace.cpp $(PKG)/host/nsb_host_capi.cpp
 HOST_HDR := $(wildcard $(PKG)/host/*.hpp) include/nsb_host.h

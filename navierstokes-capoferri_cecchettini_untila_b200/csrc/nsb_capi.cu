@@ -1,0 +1,919 @@
+// libnsb.so: the sm_100a hot path behind include/nsb.h.
+//
+//   nsb_assemble         <- NavierStokes::assemble         (reference src/NavierStokes.cpp:133-330)
+//   nsb_solve_time_step  <- NavierStokes::solve_time_step  (:344-397) + PreconditionASIMPLE (:934-995)
+//   nsb_compute_forces   <- NavierStokes::compute_forces   (:831-929)
+//
+// Host code here only sequences kernels and runs the (restart x restart)
+// Hessenberg/Givens recurrence of GMRES; all O(N) work is on the device.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "assemble.cuh"
+#include "common.cuh"
+#include "forces.cuh"
+#include "krylov.cuh"
+#include "spmv.cuh"
+
+using namespace nsb;
+
+struct nsb_ctx {
+  int dim = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t dev_bytes = 0, launches = 0;
+  // sizes
+  int64_t n_verts = 0, n_cells = 0, N = 0;
+  uint32_t n_u = 0, n_p = 0;
+  int NN = 0, NV = 0, DPC = 0, quad_rule = NSB_QUAD_DEALII95;
+  FeTables fe_host;
+  // immutable inputs
+  DevBuf<double> xyz;
+  DevBuf<uint32_t> cell_verts, cell_nodes, cell_pverts;
+  CsrDev a00, a01, a10, s;
+  std::vector<int64_t> h_rp01, h_rp10;  // kept until finalize for the symbolic S = A10*A01
+  std::vector<uint32_t> h_ci01, h_ci10;
+  DevBuf<uint16_t> slot00, slot01, slot10;
+  DevBuf<int64_t> diag00, diagS;
+  DevBuf<FeTables> fe;
+  DevBuf<int> errflag;
+  // system vectors
+  DevBuf<double> rhs, sol, di, dis, first_diag;
+  // boundary data
+  DevBuf<uint32_t> bc_dofs;
+  DevBuf<double> bc_vals;
+  double bc_factor = 1.0;
+  int bc_mode = NSB_BCDIAG_KEEP;
+  DevBuf<uint32_t> ff_cell;
+  DevBuf<double> ff_normal, ff_measure, force_out;
+  // parameters (NavierStokes.hpp:254-256, 306; NavierStokes.cpp:348, 972-973)
+  double dt = 0.01, nu = 1e-3, alpha = 0.5, rtol = 1e-6;
+  int restart = 28, max_it = 10000, prec = NSB_PREC_ASIMPLE;
+  int sweepsF = 4, sweepsS = 20;
+  double ratioF = 10.0, ratioS = 300.0;
+  // Krylov work space
+  DevBuf<double> V, tmpN, hdev, partials, coef;
+  DevBuf<unsigned> counter;
+  int V_restart = 0;
+  // preconditioner work space
+  DevBuf<double> vec0, vec1, chd_u, chz_u, chd_p, chz_p, chz_p2, eig_u, eig_p, eig_w;
+  double lamF = 0, lamS = 0;
+  bool eig_warm = false;
+  bool have_mesh = false, have_dofs = false, have_quad = false, finalized = false;
+  double t_ms[4] = {0, 0, 0, 0};
+  DevBuf<char> flush;
+  int spmv_L = 16;
+};
+
+namespace {
+
+template <class F>
+int guarded(nsb_ctx *c, F &&f) {
+  try {
+    if (c) NSB_CUDA(cudaSetDevice(c->device));
+    f();
+    return NSB_OK;
+  } catch (const CudaError &e) {
+    if (c) c->err = e.what();
+    return NSB_ECUDA;
+  } catch (const ArgError &e) {
+    if (c) c->err = e.what();
+    return NSB_EARG;
+  } catch (const StructError &e) {
+    if (c) c->err = e.what();
+    return NSB_ESTRUCT;
+  } catch (const NoConvergence &e) {
+    if (c) c->err = e.what();
+    return NSB_ENOCONV;
+  } catch (const NcclError &e) {
+    if (c) c->err = e.what();
+    return NSB_ENCCL;
+  } catch (const std::exception &e) {
+    if (c) c->err = e.what();
+    return NSB_EARG;
+  }
+}
+
+inline unsigned blocks_for(int64_t n_threads, int block = 256) { return (unsigned)((n_threads + block - 1) / block); }
+
+#define NSB_LAUNCH(c, kernel, grid, block, ...)                  \
+  do {                                                           \
+    kernel<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);    \
+    ++(c)->launches;                                             \
+    NSB_CUDA(cudaGetLastError());                                \
+  } while (0)
+
+int pick_L(const CsrDev &A) {
+  const double mean = A.n_rows ? (double)A.nnz / (double)A.n_rows : 0.0;
+  return mean < 12 ? 4 : mean < 40 ? 8 : mean < 120 ? 16 : 32;
+}
+
+// y = A x (mode 0), w - A x (1), w - d.*(A x) (2), d.*(A x) (3)
+void spmv(nsb_ctx *c, const CsrDev &A, int mode, const double *x, const double *w, const double *d, double *y) {
+  const int L = pick_L(A);
+  const unsigned grid = blocks_for(A.n_rows * L);
+  if (!A.n_rows) return;
+#define NSB_SPMV_CASE(LL, MM) \
+  if (L == LL && mode == MM) NSB_LAUNCH(c, (spmv_kernel<LL, MM>), grid, 256, A.view(), x, w, d, y)
+#define NSB_SPMV_L(LL) NSB_SPMV_CASE(LL, 0); NSB_SPMV_CASE(LL, 1); NSB_SPMV_CASE(LL, 2); NSB_SPMV_CASE(LL, 3)
+  NSB_SPMV_L(4);
+  NSB_SPMV_L(8);
+  NSB_SPMV_L(16);
+  NSB_SPMV_L(32);
+#undef NSB_SPMV_L
+#undef NSB_SPMV_CASE
+}
+
+void block_spmv(nsb_ctx *c, const double *x, double *y) {
+  const int L = c->spmv_L;
+  const unsigned grid = blocks_for(c->N * L);
+  if (L == 4) NSB_LAUNCH(c, block_spmv_kernel<4>, grid, 256, c->a00.view(), c->a01.view(), c->a10.view(), x, y);
+  if (L == 8) NSB_LAUNCH(c, block_spmv_kernel<8>, grid, 256, c->a00.view(), c->a01.view(), c->a10.view(), x, y);
+  if (L == 16) NSB_LAUNCH(c, block_spmv_kernel<16>, grid, 256, c->a00.view(), c->a01.view(), c->a10.view(), x, y);
+  if (L == 32) NSB_LAUNCH(c, block_spmv_kernel<32>, grid, 256, c->a00.view(), c->a01.view(), c->a10.view(), x, y);
+}
+
+void cheb_sweep(nsb_ctx *c, const CsrDev &M, const double *dinv, const double *b, const double *z, double *d,
+                double *znew, double c1, double c2) {
+  const int L = pick_L(M);
+  const unsigned grid = blocks_for(M.n_rows * L);
+  if (L == 4) NSB_LAUNCH(c, cheb_sweep_kernel<4>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
+  if (L == 8) NSB_LAUNCH(c, cheb_sweep_kernel<8>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
+  if (L == 16) NSB_LAUNCH(c, cheb_sweep_kernel<16>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
+  if (L == 32) NSB_LAUNCH(c, cheb_sweep_kernel<32>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
+}
+
+// out ~= M^{-1} b by a degree-k Chebyshev-Jacobi polynomial (zero initial
+// guess) targeting the interval [lmax/ratio, lmax] of D^{-1} M.
+void cheb_solve(nsb_ctx *c, const CsrDev &M, const double *dinv, const double *b, double *out, double *scratch,
+                double *d, int k, double lmax, double ratio) {
+  const int64_t n = M.n_rows;
+  const double lmin = lmax / ratio, theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  double *z = ((k - 1) % 2 == 0) ? out : scratch, *zn = ((k - 1) % 2 == 0) ? scratch : out;
+  NSB_LAUNCH(c, cheb_first_kernel, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, z);
+  double rho = 1.0 / sigma;
+  for (int i = 1; i < k; ++i) {
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    cheb_sweep(c, M, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta);
+    std::swap(z, zn);
+    rho = rho_new;
+  }
+}
+
+void multi_dot(nsb_ctx *c, const double *V, int64_t ld, int k, const double *w, int64_t n, bool with_self,
+               double *out) {
+  NSB_LAUNCH(c, multi_dot_kernel, kRedBlocks, kRedThreads, V, ld, k, w, n, with_self ? 1 : 0, out, c->partials.p,
+             c->counter.p);
+}
+void multi_axpy(nsb_ctx *c, const double *V, int64_t ld, int k, const double *coef, double sign, double *w,
+                int64_t n, bool with_norm, double *out_norm2) {
+  NSB_LAUNCH(c, multi_axpy_kernel, kRedBlocks, kRedThreads, V, ld, k, coef, sign, w, n, with_norm ? 1 : 0, out_norm2,
+             c->partials.p, c->counter.p);
+}
+
+double norm2_host(nsb_ctx *c, const double *v, int64_t n) {
+  multi_dot(c, nullptr, 0, 0, v, n, true, c->hdev.p);
+  double h;
+  NSB_CUDA(cudaMemcpyAsync(&h, c->hdev.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return std::sqrt(h);
+}
+
+__global__ void eig_seed_kernel(int64_t n, double *v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = 1.0 + 0.5 * sin(0.7 * (double)i + 0.3);
+}
+
+// lambda_max(D^-1 M) by power iteration, warm-started from `v`
+double power_lmax(nsb_ctx *c, const CsrDev &M, const double *dinv, double *v, double *w, int iters) {
+  const int64_t n = M.n_rows;
+  double *h = c->hdev.p;
+  multi_dot(c, nullptr, 0, 0, v, n, true, h);
+  NSB_LAUNCH(c, normalize_kernel, kRedBlocks, 256, n, h, v, v);
+  for (int i = 0; i < iters; ++i) {
+    spmv(c, M, 3, v, nullptr, dinv, w);
+    multi_dot(c, nullptr, 0, 0, w, n, true, h);
+    NSB_LAUNCH(c, normalize_kernel, kRedBlocks, 256, n, h, w, v);
+  }
+  double n2;
+  NSB_CUDA(cudaMemcpyAsync(&n2, h, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  return std::sqrt(n2);
+}
+
+void check_errflag(nsb_ctx *c, const char *what) {
+  int e = 0;
+  NSB_CUDA(cudaMemcpyAsync(&e, c->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  if (e) {
+    c->errflag.zero(c->stream);
+    throw StructError(std::string(what) + ": inputs do not have the Taylor-Hood P2/P1 structure (code " +
+                      std::to_string(e) + ")");
+  }
+}
+
+void upload_pattern(nsb_ctx *c, CsrDev &A, int64_t n_rows, int64_t n_cols, const int64_t *rowptr,
+                    const uint32_t *colind) {
+  if (rowptr[0] != 0) throw ArgError("nsb_set_pattern: rowptr[0] != 0");
+  A.n_rows = n_rows;
+  A.n_cols = n_cols;
+  A.nnz = rowptr[n_rows];
+  A.rowptr.upload(rowptr, (size_t)n_rows + 1, c->stream, &c->dev_bytes);
+  A.colind.upload(colind, (size_t)A.nnz, c->stream, &c->dev_bytes);
+  A.val.alloc((size_t)A.nnz, &c->dev_bytes);
+  A.val.zero(c->stream);
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  A.have = true;
+}
+
+// structural product A10*A01 on the host (runs once)
+void symbolic_schur(nsb_ctx *c) {
+  const int64_t np = c->n_p;
+  std::vector<int64_t> rp((size_t)np + 1, 0);
+  std::vector<std::vector<uint32_t>> rows((size_t)np);
+#pragma omp parallel for schedule(dynamic, 512)
+  for (int64_t V = 0; V < np; ++V) {
+    std::vector<uint32_t> buf;
+    for (int64_t k = c->h_rp10[V]; k < c->h_rp10[V + 1]; ++k) {
+      const uint32_t u = c->h_ci10[k];
+      buf.insert(buf.end(), c->h_ci01.begin() + c->h_rp01[u], c->h_ci01.begin() + c->h_rp01[u + 1]);
+    }
+    std::sort(buf.begin(), buf.end());
+    buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
+    rows[V].swap(buf);
+  }
+  for (int64_t V = 0; V < np; ++V) rp[V + 1] = rp[V] + (int64_t)rows[V].size();
+  std::vector<uint32_t> ci((size_t)rp[np]);
+  for (int64_t V = 0; V < np; ++V) std::copy(rows[V].begin(), rows[V].end(), ci.begin() + rp[V]);
+  upload_pattern(c, c->s, np, np, rp.data(), ci.data());
+}
+
+void finalize_setup(nsb_ctx *c) {
+  if (c->finalized) return;
+  if (!c->have_mesh || !c->have_dofs || !c->a00.have || !c->a01.have || !c->a10.have)
+    throw ArgError("setup incomplete: need nsb_set_mesh, nsb_set_dofs and the A00/A01/A10 patterns");
+  if (c->a00.n_rows != c->n_u || c->a01.n_rows != c->n_u || c->a10.n_rows != c->n_p)
+    throw ArgError("pattern sizes do not match n_u/n_p");
+  if (!c->have_quad) {
+    if (!fill_fe_tables(c->dim, c->quad_rule, c->fe_host)) throw ArgError("bad quadrature rule");
+    c->fe.upload(&c->fe_host, 1, c->stream, &c->dev_bytes);
+    c->have_quad = true;
+  }
+  if (!c->s.have) symbolic_schur(c);
+  c->h_rp01 = {};
+  c->h_rp10 = {};
+  c->h_ci01 = {};
+  c->h_ci10 = {};
+  const int NN = c->NN, NV = c->NV;
+  c->slot00.alloc((size_t)c->n_cells * NN * NN, &c->dev_bytes);
+  c->slot01.alloc((size_t)c->n_cells * NN * NV, &c->dev_bytes);
+  c->slot10.alloc((size_t)c->n_cells * NV * NN, &c->dev_bytes);
+  const int64_t per = NN * NN + 2 * NN * NV;
+  if (c->dim == 2)
+    NSB_LAUNCH(c, build_slots_kernel<2>, blocks_for(c->n_cells * per), 256, c->n_cells, c->cell_nodes.p,
+               c->cell_pverts.p, c->a00.view(), c->a01.view(), c->a10.view(), c->slot00.p, c->slot01.p, c->slot10.p,
+               c->errflag.p);
+  else
+    NSB_LAUNCH(c, build_slots_kernel<3>, blocks_for(c->n_cells * per), 256, c->n_cells, c->cell_nodes.p,
+               c->cell_pverts.p, c->a00.view(), c->a01.view(), c->a10.view(), c->slot00.p, c->slot01.p, c->slot10.p,
+               c->errflag.p);
+  c->diag00.alloc(c->n_u, &c->dev_bytes);
+  c->diagS.alloc(c->n_p, &c->dev_bytes);
+  NSB_LAUNCH(c, diag_positions_kernel, blocks_for(c->n_u), 256, c->a00.view(), c->diag00.p, c->errflag.p);
+  NSB_LAUNCH(c, diag_positions_kernel, blocks_for(c->n_p), 256, c->s.view(), c->diagS.p, c->errflag.p);
+  check_errflag(c, "nsb_finalize_setup");
+  const int64_t N = c->N;
+  auto dz = [&](DevBuf<double> &b, size_t n) {
+    b.alloc(n, &c->dev_bytes);
+    b.zero(c->stream);
+  };
+  dz(c->rhs, N);
+  if (!c->sol.p) dz(c->sol, N);
+  dz(c->di, c->n_u);
+  dz(c->dis, c->n_p);
+  dz(c->first_diag, 1);
+  dz(c->tmpN, N);
+  dz(c->hdev, 2 * kMaxDots + 8);
+  dz(c->partials, (size_t)kMaxDots * kRedBlocks);
+  dz(c->coef, kMaxDots);
+  c->counter.alloc(1, &c->dev_bytes);
+  c->counter.zero(c->stream);
+  dz(c->vec0, c->n_u);
+  dz(c->vec1, c->n_p);
+  dz(c->chd_u, c->n_u);
+  dz(c->chz_u, c->n_u);
+  dz(c->chd_p, c->n_p);
+  dz(c->chz_p, c->n_p);
+  dz(c->chz_p2, c->n_p);
+  dz(c->eig_u, c->n_u);
+  dz(c->eig_p, c->n_p);
+  dz(c->eig_w, c->n_u);
+  dz(c->force_out, 2);
+  NSB_LAUNCH(c, eig_seed_kernel, blocks_for(c->n_u), 256, (int64_t)c->n_u, c->eig_u.p);
+  NSB_LAUNCH(c, eig_seed_kernel, blocks_for(c->n_p), 256, (int64_t)c->n_p, c->eig_p.p);
+  const char *envL = std::getenv("NSB_SPMV_L");
+  if (envL) {
+    const int L = std::atoi(envL);
+    if (L == 4 || L == 8 || L == 16 || L == 32) c->spmv_L = L;
+  }
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  c->finalized = true;
+}
+
+void ensure_krylov(nsb_ctx *c) {
+  if (c->V_restart != c->restart || !c->V.p) {
+    c->V.alloc((size_t)(c->restart + 1) * c->N, &c->dev_bytes);
+    c->V_restart = c->restart;
+  }
+}
+
+// ---- assembly -----------------------------------------------------------
+void assemble_launch(nsb_ctx *c) {
+  AsmArgs A;
+  A.n_cells = c->n_cells;
+  A.xyz = c->xyz.p;
+  A.cell_verts = c->cell_verts.p;
+  A.cell_nodes = c->cell_nodes.p;
+  A.cell_pverts = c->cell_pverts.p;
+  A.slot00 = c->slot00.p;
+  A.slot01 = c->slot01.p;
+  A.slot10 = c->slot10.p;
+  A.rowptr00 = c->a00.rowptr.p;
+  A.rowptr01 = c->a01.rowptr.p;
+  A.rowptr10 = c->a10.rowptr.p;
+  A.val00 = c->a00.val.p;
+  A.val01 = c->a01.val.p;
+  A.val10 = c->a10.val.p;
+  A.rhs = c->rhs.p;
+  A.sol = c->sol.p;
+  A.fe = c->fe.p;
+  A.inv_dt = 1.0 / c->dt;
+  A.nu = c->nu;
+  // reference :154-156
+  c->a00.val.zero(c->stream);
+  c->a01.val.zero(c->stream);
+  c->a10.val.zero(c->stream);
+  c->rhs.zero(c->stream);
+  const unsigned grid =
+      (unsigned)std::min<int64_t>((c->n_cells + kAsmWarps - 1) / kAsmWarps, (int64_t)kNumSM * 8);
+  if (c->dim == 2)
+    NSB_LAUNCH(c, (assemble_cells_kernel<2, 7>), grid, kAsmWarps * 32, A);
+  else if (c->fe_host.nq == 10)
+    NSB_LAUNCH(c, (assemble_cells_kernel<3, 10>), grid, kAsmWarps * 32, A);
+  else
+    NSB_LAUNCH(c, (assemble_cells_kernel<3, 14>), grid, kAsmWarps * 32, A);
+  // reference :326-328
+  if (c->bc_dofs.n) {
+    NSB_LAUNCH(c, first_diag_kernel, 1, 32, c->a00.val.p, c->diag00.p, (int64_t)c->n_u, c->first_diag.p);
+    NSB_LAUNCH(c, apply_dirichlet_kernel, blocks_for((int64_t)c->bc_dofs.n * 32), 256, (int64_t)c->bc_dofs.n,
+               c->bc_dofs.p, c->bc_vals.p, c->bc_factor, c->a00.view(), c->a01.view(), c->diag00.p, c->first_diag.p,
+               c->bc_mode, c->rhs.p, c->sol.p);
+  }
+}
+
+// ---- preconditioner -------------------------------------------------------
+// PreconditionASIMPLE::initialize, reference :934-963
+void prec_init(nsb_ctx *c) {
+  NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_u), 256, (int64_t)c->n_u, c->a00.val.p, c->diag00.p, c->di.p);
+  if (c->prec != NSB_PREC_ASIMPLE) return;
+  c->s.val.zero(c->stream);
+  NSB_LAUNCH(c, schur_numeric_kernel, blocks_for((int64_t)c->n_p * 32), 256, c->a10.view(), c->a01.view(), c->di.p,
+             c->s.view());
+  NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_p), 256, (int64_t)c->n_p, c->s.val.p, c->diagS.p, c->dis.p);
+  const int its = c->eig_warm ? 6 : 30;
+  c->lamF = 1.05 * power_lmax(c, c->a00, c->di.p, c->eig_u.p, c->eig_w.p, its);
+  c->lamS = 1.05 * power_lmax(c, c->s, c->dis.p, c->eig_p.p, c->eig_w.p, its);
+  c->eig_warm = true;
+}
+
+// PreconditionASIMPLE::vmult, reference :966-995, with the two inner solves
+// replaced by Chebyshev-Jacobi polynomials of fixed degree (a linear,
+// stationary operator: no stale initial guesses).
+void prec_apply(nsb_ctx *c, const double *src, double *dst) {
+  const int64_t nu = c->n_u, np = c->n_p;
+  if (c->prec == NSB_PREC_IDENTITY) {
+    NSB_CUDA(cudaMemcpyAsync(dst, src, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return;
+  }
+  // vec0 ~= F^-1 src0                                   (:978-981)
+  cheb_solve(c, c->a00, c->di.p, src, c->vec0.p, c->chz_u.p, c->chd_u.p, c->sweepsF, c->lamF, c->ratioF);
+  // vec1 = src1 - B vec0                                 (:982-983)
+  spmv(c, c->a10, 1, c->vec0.p, src + nu, nullptr, c->vec1.p);
+  // dst1 ~= S^-1 vec1, then dst1 *= -1/alpha             (:986-990)
+  cheb_solve(c, c->s, c->dis.p, c->vec1.p, c->chz_p2.p, c->chz_p.p, c->chd_p.p, c->sweepsS, c->lamS, c->ratioS);
+  NSB_LAUNCH(c, scale_kernel, blocks_for(np), 256, np, -1.0 / c->alpha, c->chz_p2.p, dst + nu);
+  // dst0 = vec0 - Di .* (Bt dst1)                        (:992-994)
+  spmv(c, c->a01, 2, dst + nu, c->vec0.p, c->di.p, dst);
+}
+
+// ---- GMRES, reference :348-350, 377 ---------------------------
+int gmres_solve(nsb_ctx *c, double tol) {
+  ensure_krylov(c);
+  const int64_t N = c->N;
+  const int m = c->restart;
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), gamma(m + 1), ci(m), si(m), h(m + 2), h2(m + 2), y(m);
+  double *x = c->sol.p, *b = c->rhs.p, *p = c->tmpN.p, *V = c->V.p;
+  double *hd = c->hdev.p;
+  int its = 0;
+  bool iterate = true, failed = false;
+  auto check = [&](double res) {
+    if (res <= tol) return false;
+    if (its >= c->max_it) {
+      failed = true;
+      return false;
+    }
+    return true;
+  };
+  do {
+    std::fill(H.begin(), H.end(), 0.0);
+    // v0 = P^-1 (b - A x)
+    block_spmv(c, x, p);
+    NSB_LAUNCH(c, axpby_kernel, kRedBlocks, 256, N, 1.0, b, -1.0, p);
+    prec_apply(c, p, V);
+    double rho = norm2_host(c, V, N);
+    iterate = check(rho);
+    if (!iterate) break;
+    gamma[0] = rho;
+    NSB_LAUNCH(c, scale_kernel, kRedBlocks, 256, N, 1.0 / rho, V, V);
+    int dim = 0;
+    for (int j = 0; j < m && iterate; ++j) {
+      ++its;
+      double *vv = V + (size_t)(j + 1) * N;
+      block_spmv(c, V + (size_t)j * N, p);
+      prec_apply(c, p, vv);
+      dim = j + 1;
+      // CGS2: h = V^T vv; vv -= V h; h2 = V^T vv; vv -= V h2; s = ||vv||
+      multi_dot(c, V, N, dim, vv, N, false, hd);
+      multi_axpy(c, V, N, dim, hd, -1.0, vv, N, false, nullptr);
+      multi_dot(c, V, N, dim, vv, N, false, hd + kMaxDots);
+      multi_axpy(c, V, N, dim, hd + kMaxDots, -1.0, vv, N, true, hd + 2 * kMaxDots);
+      NSB_CUDA(cudaMemcpyAsync(h.data(), hd, sizeof(double) * dim, cudaMemcpyDeviceToHost, c->stream));
+      NSB_CUDA(cudaMemcpyAsync(h2.data(), hd + kMaxDots, sizeof(double) * dim, cudaMemcpyDeviceToHost, c->stream));
+      double s2;
+      NSB_CUDA(cudaMemcpyAsync(&s2, hd + 2 * kMaxDots, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      NSB_CUDA(cudaStreamSynchronize(c->stream));
+      for (int i = 0; i < dim; ++i) h[i] += h2[i];
+      const double s = std::sqrt(s2);
+      h[j + 1] = s;
+      if (std::isfinite(1.0 / s)) NSB_LAUNCH(c, scale_kernel, kRedBlocks, 256, N, 1.0 / s, vv, vv);
+      for (int i = 0; i < j; ++i) {
+        const double d = h[i];
+        h[i] = ci[i] * d + si[i] * h[i + 1];
+        h[i + 1] = -si[i] * d + ci[i] * h[i + 1];
+      }
+      const double r = 1.0 / std::sqrt(h[j] * h[j] + h[j + 1] * h[j + 1]);
+      si[j] = h[j + 1] * r;
+      ci[j] = h[j] * r;
+      h[j] = ci[j] * h[j] + si[j] * h[j + 1];
+      gamma[j + 1] = -si[j] * gamma[j];
+      gamma[j] *= ci[j];
+      for (int i = 0; i < dim; ++i) H[(size_t)i * m + j] = h[i];
+      rho = std::fabs(gamma[dim]);
+      iterate = check(rho);
+    }
+    for (int i = dim - 1; i >= 0; --i) {
+      double s = gamma[i];
+      for (int k = i + 1; k < dim; ++k) s -= H[(size_t)i * m + k] * y[k];
+      y[i] = s / H[(size_t)i * m + i];
+    }
+    if (dim > 0) {
+      NSB_CUDA(cudaMemcpyAsync(c->coef.p, y.data(), sizeof(double) * dim, cudaMemcpyHostToDevice, c->stream));
+      multi_axpy(c, V, N, dim, c->coef.p, 1.0, x, N, false, nullptr);
+      NSB_CUDA(cudaStreamSynchronize(c->stream));  // y is reused by the next cycle
+    }
+  } while (iterate);
+  if (failed) return -its;
+  return its;
+}
+
+}  // namespace
+
+// ==========================================================================
+extern "C" {
+
+const char *nsb_last_error(const nsb_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int nsb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int nsb_create(int dim, int device_id, nsb_ctx **out) {
+  if (!out || (dim != 2 && dim != 3)) return NSB_EARG;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device_id < 0 || device_id >= n) {
+    cudaGetLastError();
+    return NSB_ECUDA;
+  }
+  nsb_ctx *c = new nsb_ctx;
+  c->dim = dim;
+  c->device = device_id;
+  c->NV = dim + 1;
+  c->NN = dim == 2 ? 6 : 10;
+  c->DPC = dim * c->NN + c->NV;
+  const int rc = guarded(c, [&] {
+    NSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    NSB_CUDA(cudaEventCreate(&c->ev0));
+    NSB_CUDA(cudaEventCreate(&c->ev1));
+    c->errflag.alloc(1, &c->dev_bytes);
+    c->errflag.zero(c->stream);
+  });
+  if (rc != NSB_OK) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return NSB_OK;
+}
+
+void nsb_destroy(nsb_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  cudaStream_t s = c->stream;
+  delete c;
+  if (s) cudaStreamDestroy(s);
+}
+
+int nsb_set_mesh(nsb_ctx *c, int64_t n_verts, const double *xyz, int64_t n_cells, const uint32_t *cell_verts) {
+  return guarded(c, [&] {
+    if (n_verts <= 0 || n_cells <= 0 || !xyz || !cell_verts) throw ArgError("nsb_set_mesh: empty mesh");
+    c->n_verts = n_verts;
+    c->n_cells = n_cells;
+    c->xyz.upload(xyz, (size_t)n_verts * c->dim, c->stream, &c->dev_bytes);
+    c->cell_verts.upload(cell_verts, (size_t)n_cells * c->NV, c->stream, &c->dev_bytes);
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_mesh = true;
+    c->finalized = false;
+  });
+}
+
+int nsb_set_dofs(nsb_ctx *c, uint32_t n_u, uint32_t n_p, const uint32_t *cell_dofs) {
+  return guarded(c, [&] {
+    if (!c->have_mesh) throw ArgError("nsb_set_dofs: call nsb_set_mesh first");
+    if (n_u % c->dim != 0 || !cell_dofs) throw ArgError("nsb_set_dofs: n_u must be a multiple of dim");
+    c->n_u = n_u;
+    c->n_p = n_p;
+    c->N = (int64_t)n_u + n_p;
+    DevBuf<uint32_t> cd;
+    cd.upload(cell_dofs, (size_t)c->n_cells * c->DPC, c->stream);
+    c->cell_nodes.alloc((size_t)c->n_cells * c->NN, &c->dev_bytes);
+    c->cell_pverts.alloc((size_t)c->n_cells * c->NV, &c->dev_bytes);
+    if (c->dim == 2)
+      NSB_LAUNCH(c, split_cell_dofs_kernel<2>, blocks_for(c->n_cells), 256, c->n_cells, cd.p, n_u, n_p,
+                 c->cell_nodes.p, c->cell_pverts.p, c->errflag.p);
+    else
+      NSB_LAUNCH(c, split_cell_dofs_kernel<3>, blocks_for(c->n_cells), 256, c->n_cells, cd.p, n_u, n_p,
+                 c->cell_nodes.p, c->cell_pverts.p, c->errflag.p);
+    check_errflag(c, "nsb_set_dofs");
+    c->have_dofs = true;
+    c->finalized = false;
+  });
+}
+
+int nsb_set_pattern(nsb_ctx *c, int block, int64_t n_rows, const int64_t *rowptr, const uint32_t *colind) {
+  return guarded(c, [&] {
+    if (!c->have_dofs) throw ArgError("nsb_set_pattern: call nsb_set_dofs first");
+    if (!rowptr || !colind || n_rows <= 0) throw ArgError("nsb_set_pattern: null input");
+    const int64_t nu = c->n_u, np = c->n_p;
+    switch (block) {
+      case NSB_A00:
+        if (n_rows != nu) throw ArgError("A00 must have n_u rows");
+        upload_pattern(c, c->a00, nu, nu, rowptr, colind);
+        break;
+      case NSB_A01:
+        if (n_rows != nu) throw ArgError("A01 must have n_u rows");
+        upload_pattern(c, c->a01, nu, np, rowptr, colind);
+        c->h_rp01.assign(rowptr, rowptr + n_rows + 1);
+        c->h_ci01.assign(colind, colind + rowptr[n_rows]);
+        break;
+      case NSB_A10:
+        if (n_rows != np) throw ArgError("A10 must have n_p rows");
+        upload_pattern(c, c->a10, np, nu, rowptr, colind);
+        c->h_rp10.assign(rowptr, rowptr + n_rows + 1);
+        c->h_ci10.assign(colind, colind + rowptr[n_rows]);
+        break;
+      case NSB_S:
+        if (n_rows != np) throw ArgError("S must have n_p rows");
+        upload_pattern(c, c->s, np, np, rowptr, colind);
+        break;
+      default:
+        throw ArgError("nsb_set_pattern: unknown block");
+    }
+    c->finalized = false;
+  });
+}
+
+int nsb_set_node_pattern(nsb_ctx *c, int64_t n_nodes, const int64_t *rowptr, const uint32_t *colind) {
+  return guarded(c, [&] {
+    if (!c->have_dofs) throw ArgError("nsb_set_node_pattern: call nsb_set_dofs first");
+    if (n_nodes * c->dim != (int64_t)c->n_u) throw ArgError("nsb_set_node_pattern: n_nodes*dim != n_u");
+    const int d = c->dim;
+    DevBuf<int64_t> nptr;
+    DevBuf<uint32_t> ncol;
+    nptr.upload(rowptr, (size_t)n_nodes + 1, c->stream);
+    ncol.upload(colind, (size_t)rowptr[n_nodes], c->stream);
+    CsrDev &A = c->a00;
+    A.n_rows = A.n_cols = c->n_u;
+    A.nnz = rowptr[n_nodes] * d * d;
+    A.rowptr.alloc((size_t)c->n_u + 1, &c->dev_bytes);
+    A.colind.alloc((size_t)A.nnz, &c->dev_bytes);
+    A.val.alloc((size_t)A.nnz, &c->dev_bytes);
+    A.val.zero(c->stream);
+    if (d == 2)
+      NSB_LAUNCH(c, expand_node_pattern_kernel<2>, blocks_for(n_nodes * 32), 256, n_nodes, nptr.p, ncol.p,
+                 A.rowptr.p, A.colind.p);
+    else
+      NSB_LAUNCH(c, expand_node_pattern_kernel<3>, blocks_for(n_nodes * 32), 256, n_nodes, nptr.p, ncol.p,
+                 A.rowptr.p, A.colind.p);
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+    A.have = true;
+    c->finalized = false;
+  });
+}
+
+int nsb_set_quadrature(nsb_ctx *c, int rule_id) {
+  return guarded(c, [&] {
+    if (!fill_fe_tables(c->dim, rule_id, c->fe_host) || (rule_id != 0 && rule_id != 1))
+      throw ArgError("nsb_set_quadrature: unknown rule");
+    c->quad_rule = rule_id;
+    c->fe.upload(&c->fe_host, 1, c->stream, &c->dev_bytes);
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_quad = true;
+  });
+}
+
+int nsb_finalize_setup(nsb_ctx *c) {
+  return guarded(c, [&] { finalize_setup(c); });
+}
+
+int nsb_set_params(nsb_ctx *c, double deltat, double nu) {
+  return guarded(c, [&] {
+    if (!(deltat > 0)) throw ArgError("nsb_set_params: deltat must be positive");
+    c->dt = deltat;
+    c->nu = nu;
+  });
+}
+int nsb_set_bc_diag_mode(nsb_ctx *c, int mode) {
+  return guarded(c, [&] {
+    if (mode != NSB_BCDIAG_KEEP && mode != NSB_BCDIAG_FIRST) throw ArgError("bad bc diag mode");
+    c->bc_mode = mode;
+  });
+}
+int nsb_set_solver(nsb_ctx *c, double gmres_rtol, int restart, int max_it, double alpha, int preconditioner) {
+  return guarded(c, [&] {
+    if (restart < 1 || restart > kMaxDots - 2) throw ArgError("nsb_set_solver: restart out of range [1,62]");
+    if (preconditioner != NSB_PREC_ASIMPLE && preconditioner != NSB_PREC_IDENTITY) throw ArgError("bad preconditioner");
+    c->rtol = gmres_rtol;
+    c->restart = restart;
+    c->max_it = max_it;
+    c->alpha = alpha;
+    c->prec = preconditioner;
+  });
+}
+int nsb_set_inner(nsb_ctx *c, int sweeps_F, double eig_ratio_F, int sweeps_S, double eig_ratio_S) {
+  return guarded(c, [&] {
+    if (sweeps_F < 1 || sweeps_S < 1 || !(eig_ratio_F > 1) || !(eig_ratio_S > 1))
+      throw ArgError("nsb_set_inner: sweeps >= 1 and eig ratios > 1 required");
+    c->sweepsF = sweeps_F;
+    c->ratioF = eig_ratio_F;
+    c->sweepsS = sweeps_S;
+    c->ratioS = eig_ratio_S;
+  });
+}
+
+int nsb_set_solution(nsb_ctx *c, const double *x) {
+  return guarded(c, [&] {
+    if (!c->have_dofs) throw ArgError("nsb_set_solution: call nsb_set_dofs first");
+    c->sol.upload(x, (size_t)c->N, c->stream, &c->dev_bytes);
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+int nsb_get_solution(nsb_ctx *c, double *x) {
+  return guarded(c, [&] {
+    if (!c->sol.p) throw ArgError("nsb_get_solution: no solution yet");
+    c->sol.download(x, c->stream);
+  });
+}
+int nsb_set_dirichlet(nsb_ctx *c, int64_t n_bc, const uint32_t *dofs, const double *values) {
+  return guarded(c, [&] {
+    if (n_bc < 0 || (n_bc > 0 && (!dofs || !values))) throw ArgError("nsb_set_dirichlet: null input");
+    c->bc_dofs.upload(dofs, (size_t)n_bc, c->stream, &c->dev_bytes);
+    c->bc_vals.upload(values, (size_t)n_bc, c->stream, &c->dev_bytes);
+    c->bc_factor = 1.0;
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+int nsb_scale_dirichlet(nsb_ctx *c, double factor) {
+  return guarded(c, [&] { c->bc_factor = factor; });
+}
+int nsb_set_force_faces(nsb_ctx *c, int64_t n_faces, const uint32_t *cell, const double *normal,
+                        const double *measure) {
+  return guarded(c, [&] {
+    c->ff_cell.upload(cell, (size_t)n_faces, c->stream, &c->dev_bytes);
+    c->ff_normal.upload(normal, (size_t)n_faces * c->dim, c->stream, &c->dev_bytes);
+    c->ff_measure.upload(measure, (size_t)n_faces, c->stream, &c->dev_bytes);
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int nsb_assemble(nsb_ctx *c, double time) {
+  (void)time;  // the forcing term is identically zero (NavierStokes.hpp:56-65); inlet time enters via nsb_scale_dirichlet
+  return guarded(c, [&] {
+    finalize_setup(c);
+    NSB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    assemble_launch(c);
+    NSB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+    float ms;
+    NSB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->t_ms[0] = ms;
+  });
+}
+
+int nsb_solve_time_step(nsb_ctx *c, int *iters, double *t_prec, double *t_solve) {
+  return guarded(c, [&] {
+    if (!c->finalized) throw ArgError("nsb_solve_time_step: nothing assembled");
+    auto t0 = std::chrono::high_resolution_clock::now();
+    const double tol = c->rtol * norm2_host(c, c->rhs.p, c->N);  // reference :348
+    prec_init(c);                                                 // reference :355-361
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+    auto t1 = std::chrono::high_resolution_clock::now();
+    const int its = gmres_solve(c, tol);  // reference :377
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+    auto t2 = std::chrono::high_resolution_clock::now();
+    const double tp = std::chrono::duration<double>(t1 - t0).count(), ts = std::chrono::duration<double>(t2 - t1).count();
+    c->t_ms[1] = 1e3 * tp;
+    c->t_ms[2] = 1e3 * ts;
+    if (iters) *iters = std::abs(its);
+    if (t_prec) *t_prec = tp;
+    if (t_solve) *t_solve = ts;
+    if (its < 0) throw NoConvergence("GMRES did not reach the tolerance within max_it iterations");
+  });
+}
+
+int nsb_compute_forces(nsb_ctx *c, double u_mean, double out[4]) {
+  return guarded(c, [&] {
+    if (!c->finalized) throw ArgError("nsb_compute_forces: setup incomplete");
+    NSB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    c->force_out.zero(c->stream);
+    const int64_t nf = (int64_t)c->ff_cell.n;
+    if (nf > 0) {
+      const unsigned grid = (unsigned)std::min<int64_t>((nf + 127) / 128, kNumSM * 4);
+      if (c->dim == 2)
+        NSB_LAUNCH(c, forces_kernel<2>, grid, 128, nf, c->ff_cell.p, c->ff_normal.p, c->ff_measure.p, c->xyz.p,
+                   c->cell_verts.p, c->cell_nodes.p, c->cell_pverts.p, c->sol.p, c->n_u, c->fe.p, c->nu,
+                   c->force_out.p);
+      else
+        NSB_LAUNCH(c, forces_kernel<3>, grid, 128, nf, c->ff_cell.p, c->ff_normal.p, c->ff_measure.p, c->xyz.p,
+                   c->cell_verts.p, c->cell_nodes.p, c->cell_pverts.p, c->sol.p, c->n_u, c->fe.p, c->nu,
+                   c->force_out.p);
+    }
+    NSB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    double dl[2];
+    c->force_out.download(dl, c->stream);
+    float ms;
+    NSB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->t_ms[3] = ms;
+    const double Diameter = 0.4;  // NavierStokes.hpp:256
+    const double den = u_mean * u_mean * Diameter * (c->dim == 3 ? 0.41 : 1.0);  // reference :913-922
+    out[0] = dl[0];
+    out[1] = dl[1];
+    out[2] = 2.0 * -dl[0] / den;
+    out[3] = 2.0 * -dl[1] / den;
+  });
+}
+
+static CsrDev *block_of(nsb_ctx *c, int block) {
+  switch (block) {
+    case NSB_A00: return &c->a00;
+    case NSB_A01: return &c->a01;
+    case NSB_A10: return &c->a10;
+    case NSB_S: return &c->s;
+  }
+  return nullptr;
+}
+
+int nsb_get_matrix_values(nsb_ctx *c, int block, double *vals) {
+  return guarded(c, [&] {
+    CsrDev *A = block_of(c, block);
+    if (!A || !A->have) throw ArgError("nsb_get_matrix_values: block not set");
+    A->val.download(vals, c->stream);
+  });
+}
+int nsb_get_pattern(nsb_ctx *c, int block, int64_t *rowptr, uint32_t *colind) {
+  return guarded(c, [&] {
+    CsrDev *A = block_of(c, block);
+    if (!A || !A->have) throw ArgError("nsb_get_pattern: block not set");
+    A->rowptr.download(rowptr, c->stream);
+    A->colind.download(colind, c->stream);
+  });
+}
+int64_t nsb_nnz(const nsb_ctx *c, int block) {
+  const CsrDev *A = block_of(const_cast<nsb_ctx *>(c), block);
+  return A && A->have ? A->nnz : -1;
+}
+int nsb_get_rhs(nsb_ctx *c, double *rhs) {
+  return guarded(c, [&] {
+    if (!c->rhs.p) throw ArgError("nsb_get_rhs: setup incomplete");
+    c->rhs.download(rhs, c->stream);
+  });
+}
+int nsb_vmult(nsb_ctx *c, const double *x, double *y) {
+  return guarded(c, [&] {
+    finalize_setup(c);
+    ensure_krylov(c);
+    NSB_CUDA(cudaMemcpyAsync(c->V.p, x, (size_t)c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    block_spmv(c, c->V.p, c->tmpN.p);
+    c->tmpN.download(y, c->stream);
+  });
+}
+
+int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
+  return guarded(c, [&] {
+    if (!c->finalized || reps < 1) throw ArgError("nsb_bench_kernel: setup incomplete or reps < 1");
+    ensure_krylov(c);
+    const bool flush = (which & 0x100) != 0;
+    which &= 0xff;
+    if (flush && !c->flush.p) c->flush.alloc((size_t)256 << 20, &c->dev_bytes);
+    double total = 0;
+    for (int r = 0; r < reps; ++r) {
+      if (flush) NSB_CUDA(cudaMemsetAsync(c->flush.p, r & 0xff, c->flush.n, c->stream));
+      NSB_CUDA(cudaEventRecord(c->ev0, c->stream));
+      switch (which) {
+        case 0: block_spmv(c, c->sol.p, c->tmpN.p); break;
+        case 1: assemble_launch(c); break;
+        case 2: prec_apply(c, c->rhs.p, c->V.p); break;
+        case 3:
+          c->s.val.zero(c->stream);
+          NSB_LAUNCH(c, schur_numeric_kernel, blocks_for((int64_t)c->n_p * 32), 256, c->a10.view(), c->a01.view(),
+                     c->di.p, c->s.view());
+          break;
+        case 4: cheb_sweep(c, c->a00, c->di.p, c->rhs.p, c->vec0.p, c->chd_u.p, c->chz_u.p, 0.5, 0.5); break;
+        default: throw ArgError("nsb_bench_kernel: unknown kernel id");
+      }
+      NSB_CUDA(cudaEventRecord(c->ev1, c->stream));
+      NSB_CUDA(cudaStreamSynchronize(c->stream));
+      float ms;
+      NSB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+      total += ms;
+    }
+    *ms_mean = total / reps;
+  });
+}
+
+int64_t nsb_launch_count(const nsb_ctx *c) { return c ? c->launches : 0; }
+int nsb_timers(const nsb_ctx *c, double out_ms[4]) {
+  if (!c) return NSB_EARG;
+  for (int i = 0; i < 4; ++i) out_ms[i] = c->t_ms[i];
+  return NSB_OK;
+}
+int nsb_info(const nsb_ctx *c, int64_t out[9]) {
+  if (!c) return NSB_EARG;
+  out[0] = c->n_u;
+  out[1] = c->n_p;
+  out[2] = c->n_cells;
+  out[3] = c->a00.nnz;
+  out[4] = c->a01.nnz;
+  out[5] = c->a10.nnz;
+  out[6] = c->s.nnz;
+  out[7] = c->fe_host.nq;
+  out[8] = c->dev_bytes;
+  return NSB_OK;
+}
+
+void *nsb_alloc_pinned(int64_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void nsb_free_pinned(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int nsb_comm_unique_id(char id[128]) {
+  (void)id;
+  return NSB_ENCCL;
+}
+int nsb_comm_init(nsb_ctx *c, int rank, int n_ranks, const char id[128]) {
+  (void)rank;
+  (void)n_ranks;
+  (void)id;
+  if (c) c->err = "multi-GPU communicator not built in this revision";
+  return NSB_ENCCL;
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// CSR sparse matrix-vector kernels on the canonical (reference) block pattern.
+//
+// Replaces TrilinosWrappers::BlockSparseMatrix::vmult / SparseMatrix::vmult as
+// used inside SolverGMRES and PreconditionASIMPLE::vmult (reference
+// src/NavierStokes.cpp:377, 982, 992).  Everything here is HBM-bound: per
+// non-zero 8 B value + 4 B column index are streamed once (ld.global.nc,
+// evict-first), x is gathered through L2.  Rows are long (A00 ~81, A10 ~169,
+// S ~53 non-zeros in 3D), so a sub-warp of L lanes walks one row with
+// coalesced 8*L-byte segments and finishes with a shuffle reduction.
+#pragma once
+#include "common.cuh"
+
+namespace nsb {
+
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) { return __ldcs(p); }
+
+// partial dot product of one CSR row with x over the lanes of a sub-warp
+template <int L>
+__device__ __forceinline__ double row_dot(const CsrView &A, int64_t row, const double *__restrict__ x, int sub) {
+  const int64_t b = __ldg(A.rowptr + row), e = __ldg(A.rowptr + row + 1);
+  double s0 = 0, s1 = 0;
+  int64_t k = b + sub;
+  for (; k + L < e; k += 2 * L) {
+    const double v0 = ld_stream(A.val + k), v1 = ld_stream(A.val + k + L);
+    const uint32_t c0 = ld_stream(A.colind + k), c1 = ld_stream(A.colind + k + L);
+    s0 += v0 * __ldg(x + c0);
+    s1 += v1 * __ldg(x + c1);
+  }
+  if (k < e) s0 += ld_stream(A.val + k) * __ldg(x + ld_stream(A.colind + k));
+  return s0 + s1;
+}
+
+template <int L>
+__device__ __forceinline__ double sub_reduce(double s) {
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// y = [A00 x_u + A01 x_p ; A10 x_u]   (A11 is empty)
+template <int L>
+__global__ void __launch_bounds__(256) block_spmv_kernel(CsrView a00, CsrView a01, CsrView a10,
+                                                         const double *__restrict__ x, double *__restrict__ y) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int sub = threadIdx.x % L;
+  const int64_t n_u = a00.n_rows, N = n_u + a10.n_rows;
+  double s = 0;  // lanes past the end stay for the full-mask shuffles
+  if (g < n_u)
+    s = row_dot<L>(a00, g, x, sub) + row_dot<L>(a01, g, x + n_u, sub);
+  else if (g < N)
+    s = row_dot<L>(a10, g - n_u, x, sub);
+  s = sub_reduce<L>(s);
+  if (sub == 0 && g < N) y[g] = s;
+}
+
+// Generic single-block product with a fused epilogue:
+//   mode 0: y = A x
+//   mode 1: y = w - A x                     (vec1 = src1 - B vec0, reference :982-983)
+//   mode 2: y = w - d .* (A x)              (dst0 = vec0 - Di .* (Bt dst1), reference :992-994)
+//   mode 3: y = d .* (A x)                  (power iteration on D^-1 A)
+template <int L, int MODE>
+__global__ void __launch_bounds__(256) spmv_kernel(CsrView A, const double *__restrict__ x,
+                                                   const double *__restrict__ w, const double *__restrict__ d,
+                                                   double *__restrict__ y) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int sub = threadIdx.x % L;
+  const bool live = g < A.n_rows;
+  const double s = sub_reduce<L>(live ? row_dot<L>(A, g, x, sub) : 0.0);
+  if (sub == 0 && live) {
+    if (MODE == 0) y[g] = s;
+    if (MODE == 1) y[g] = w[g] - s;
+    if (MODE == 2) y[g] = w[g] - d[g] * s;
+    if (MODE == 3) y[g] = d[g] * s;
+  }
+}
+
+// One Chebyshev-Jacobi sweep for M z = b (the Jacobi-type inner sweep that
+// replaces ILU + inner GMRES, reference :978-981, 986-989):
+//   dnew = c1 * d + c2 * Dinv .* (b - M z);  znew = z + dnew
+// z and znew are distinct buffers (the product gathers z).
+template <int L>
+__global__ void __launch_bounds__(256) cheb_sweep_kernel(CsrView M, const double *__restrict__ dinv,
+                                                         const double *__restrict__ b, const double *__restrict__ z,
+                                                         double *__restrict__ d, double *__restrict__ znew, double c1,
+                                                         double c2) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int sub = threadIdx.x % L;
+  const bool live = g < M.n_rows;
+  const double s = sub_reduce<L>(live ? row_dot<L>(M, g, z, sub) : 0.0);
+  if (sub == 0 && live) {
+    const double dn = c1 * d[g] + c2 * dinv[g] * (b[g] - s);
+    d[g] = dn;
+    znew[g] = z[g] + dn;
+  }
+}
+
+// first sweep with zero initial guess: d = z = Dinv .* b / theta
+__global__ void cheb_first_kernel(int64_t n, const double *__restrict__ dinv, const double *__restrict__ b,
+                                  double inv_theta, double *__restrict__ d, double *__restrict__ z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double v = dinv[i] * b[i] * inv_theta;
+    d[i] = v;
+    z[i] = v;
+  }
+}
+
+__global__ void diag_inverse_kernel(int64_t n, const double *__restrict__ val, const int64_t *__restrict__ diagpos,
+                                    double *__restrict__ dinv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dinv[i] = 1.0 / val[diagpos[i]];
+}
+
+// S = B diag(Di) Bt on the precomputed pattern of S (reference :956).  One warp
+// per row V of B = A10; lanes stride over the row's entries u and scatter
+// B[V,u] Di[u] Bt[u,W] into S[V,W] (position by binary search in row V of S).
+__global__ void __launch_bounds__(256) schur_numeric_kernel(CsrView B, CsrView Bt, const double *__restrict__ di,
+                                                            CsrView S) {
+  const int64_t V = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (V >= B.n_rows) return;
+  const int64_t sb = S.rowptr[V], se = S.rowptr[V + 1];
+  for (int64_t k = B.rowptr[V] + lane; k < B.rowptr[V + 1]; k += 32) {
+    const uint32_t u = B.colind[k];
+    const double coef = B.val[k] * di[u];
+    for (int64_t kk = Bt.rowptr[u]; kk < Bt.rowptr[u + 1]; ++kk) {
+      const double t = Bt.val[kk];
+      if (t == 0.0) continue;  // constrained rows of Bt are zero
+      const uint32_t W = Bt.colind[kk];
+      int64_t lo = sb, hi = se;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (S.colind[mid] < W)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      atomicAdd(S.val + lo, coef * t);
+    }
+  }
+}
+
+}  // namespace nsb
