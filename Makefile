@@ -15,7 +15,7 @@ HOST_HDR := $(wildcard $(PKG)/host/*.hpp) include/nsb_host.h
 CU_SRC   := $(PKG)/csrc/nsb_capi.cu
 CU_HDR   := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/nsb.h
 
-all: host oracle cuda drivers
+all: host oracle cuda
 
 host: $(PKG)/libnsb_host.so
 oracle: oracle/libns_oracle.so
