@@ -15,7 +15,7 @@ HOST_HDR := $(wildcard $(PKG)/host/*.hpp) include/nsb_host.h
 CU_SRC   := $(PKG)/csrc/nsb_capi.cu
 CU_HDR   := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/nsb.h
 
-all: host oracle cuda
+all: host oracle cuda drivers
 
 host: $(PKG)/libnsb_host.so
 oracle: oracle/libns_oracle.so
@@ -30,12 +30,19 @@ oracle/libns_oracle.so: oracle/ns_oracle.cpp oracle/ns_oracle.h
 $(PKG)/libnsb.so: $(CU_SRC) $(CU_HDR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRC) -cudart static -ldl 2> $(PKG)/csrc/ptxas.log || (cat $(PKG)/csrc/ptxas.log; false)
 
-DRIVER_SRC := $(wildcard $(PKG)/drivers/*.cpp)
-DRIVER_BIN := $(DRIVER_SRC:.cpp=)
+DRV      := $(PKG)/drivers
+DRIVER_BIN := $(DRV)/d2_test_01 $(DRV)/d2_test_02 $(DRV)/d2_test_03 $(DRV)/d2_test_naca \
+              $(DRV)/d3_test_01 $(DRV)/d3_test_02 $(DRV)/d3_test_03 $(DRV)/make_mesh
+FACADE   := $(PKG)/host/NavierStokes.cpp $(PKG)/host/NavierStokes.hpp $(DRV)/driver_common.hpp
 drivers: $(DRIVER_BIN)
-$(PKG)/drivers/%: $(PKG)/drivers/%.cpp $(PKG)/host/NavierStokes.cpp $(PKG)/host/NavierStokes.hpp $(PKG)/libnsb_host.so $(PKG)/libnsb.so
-	$(CXX) $(CXXFLAGS) -I$(PKG)/host -Iinclude -o $@ $< $(PKG)/host/NavierStokes.cpp \
+$(DRV)/d2_%: $(DRV)/d2_%.cpp $(FACADE) $(PKG)/libnsb_host.so $(PKG)/libnsb.so
+	$(CXX) $(CXXFLAGS) -fPIE -DDIM=2 -I$(PKG)/host -Iinclude -o $@ $< $(PKG)/host/NavierStokes.cpp \
 	    -L$(PKG) -lnsb_host -lnsb -Wl,-rpath,'$$ORIGIN/..'
+$(DRV)/d3_%: $(DRV)/d3_%.cpp $(FACADE) $(PKG)/libnsb_host.so $(PKG)/libnsb.so
+	$(CXX) $(CXXFLAGS) -fPIE -DDIM=3 -I$(PKG)/host -Iinclude -o $@ $< $(PKG)/host/NavierStokes.cpp \
+	    -L$(PKG) -lnsb_host -lnsb -Wl,-rpath,'$$ORIGIN/..'
+$(DRV)/make_mesh: $(DRV)/make_mesh.cpp $(PKG)/libnsb_host.so
+	$(CXX) $(CXXFLAGS) -fPIE -I$(PKG)/host -o $@ $< -L$(PKG) -lnsb_host -Wl,-rpath,'$$ORIGIN/..'
 
 clean:
 	rm -f $(PKG)/*.so oracle/*.so $(DRIVER_BIN) $(PKG)/csrc/ptxas.log

@@ -1,0 +1,329 @@
+// Facade implementation: the reference's method sequence (reference
+// src/NavierStokes.cpp) expressed through include/nsb.h + the host setup
+// library.  Console and CSV output follow the reference byte for byte where it
+// is part of the de-facto interface (forces_vs_time.csv).
+#include "NavierStokes.hpp"
+
+#include <chrono>
+#include <cstdlib>
+#include <iomanip>
+
+#include "../../include/nsb.h"
+#include "problem.hpp"
+
+namespace {
+unsigned int env_uint(const char *name, unsigned int dflt) {
+  const char *v = std::getenv(name);
+  return v ? (unsigned int)std::strtoul(v, nullptr, 10) : dflt;
+}
+}  // namespace
+
+NavierStokes::NavierStokes(const std::string &mesh_file_name_, const unsigned int &degree_velocity_,
+                           const unsigned int &degree_pressure_, const double &deltat_, const double &T_,
+                           const unsigned int &step_)
+    : mesh_file_name(mesh_file_name_),
+      mpi_size(env_uint("WORLD_SIZE", 1)),
+      mpi_rank(env_uint("RANK", 0)),
+      degree_velocity(degree_velocity_),
+      degree_pressure(degree_pressure_),
+      deltat(deltat_),
+      T(T_),
+      step(step_) {
+  if (degree_velocity != 2 || degree_pressure != 1)
+    throw std::invalid_argument("NavierStokes: only the Taylor-Hood pair P2/P1 of the reference drivers is built");
+}
+
+NavierStokes::~NavierStokes() {
+  if (ctx) nsb_destroy(ctx);
+}
+
+void NavierStokes::check(int rc, const char *what) const {
+  if (rc == NSB_OK) return;
+  // the reference lets deal.II exceptions escape to the driver
+  throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " +
+                           (ctx ? nsb_last_error(ctx) : "no context"));
+}
+
+// reference :4-131
+void NavierStokes::setup() {
+  const bool pcout = mpi_rank == 0;
+  if (pcout) std::cout << "Importing the mesh from " << mesh_file_name << std::endl;
+  problem = std::make_unique<nsb::Problem>();
+  problem->mesh = nsb::read_msh(mesh_file_name, dim);  // throws like GridIn::read_msh
+  if (pcout) {
+    std::cout << "\tNumber of elements = " << problem->mesh.n_cells() << std::endl;
+    std::cout << "---------------------------------------------------" << std::endl;
+    std::cout << "Initializing the finite element spaces" << std::endl;
+  }
+  problem->build_space(/*expand_a00=*/false);
+  const nsb::DofMap &d = problem->dofs;
+  if (pcout) {
+    std::cout << "\tVelocity degree:\t\t" << degree_velocity << std::endl;
+    std::cout << "\tPressure degree:\t\t" << degree_pressure << std::endl;
+    std::cout << "\tDoFs per cell:\t\t\t" << d.dofs_per_cell() << std::endl;
+    std::cout << "\tQuadrature points per cell:\t" << (dim == 2 ? 7 : (quad_rule == 0 ? 10 : 14)) << std::endl;
+    std::cout << "\tQuadrature points per face:\t" << (dim == 2 ? 3 : 7) << std::endl;
+    std::cout << "---------------------------------------------------" << std::endl;
+    std::cout << "Initializing the DoF handler" << std::endl;
+    std::cout << "\tNumber of DoFs:" << std::endl;
+    std::cout << "\t\tvelocity:\t\t" << d.n_u << std::endl;
+    std::cout << "\t\tpressure:\t\t" << d.n_p << std::endl;
+    std::cout << "\t\ttotal:\t\t\t" << d.n_u + d.n_p << std::endl;
+    std::cout << "---------------------------------------------------" << std::endl;
+    std::cout << "Initializing the linear system" << std::endl;
+    std::cout << "\tInitializing the sparsity pattern" << std::endl;
+  }
+  // boundary lists: dof set once, values re-evaluated per step through the
+  // driver's InletVelocity (reference :297-324)
+  problem->bfaces = nsb::boundary_faces(problem->mesh);
+  problem->ff = nsb::force_faces(problem->mesh, problem->bfaces, 4);
+  refresh_dirichlet(0.0);
+
+  const int device = (int)env_uint("LOCAL_RANK", 0);
+  if (nsb_create(dim, device, &ctx) != NSB_OK)
+    throw std::runtime_error("NavierStokes::setup: no usable CUDA device (there is no CPU path)");
+  const nsb::Mesh &m = problem->mesh;
+  const nsb::Patterns &P = problem->pat;
+  check(nsb_set_mesh(ctx, (int64_t)m.n_verts(), m.xyz.data(), (int64_t)m.n_cells(), m.cells.data()), "nsb_set_mesh");
+  check(nsb_set_dofs(ctx, d.n_u, d.n_p, d.cell_dofs.data()), "nsb_set_dofs");
+  if (pcout) std::cout << "\tInitializing the matrices" << std::endl;
+  check(nsb_set_node_pattern(ctx, P.nodes.n_rows, P.nodes.rowptr.data(), P.nodes.colind.data()), "nsb_set_node_pattern");
+  check(nsb_set_pattern(ctx, NSB_A01, P.a01.n_rows, P.a01.rowptr.data(), P.a01.colind.data()), "nsb_set_pattern(A01)");
+  check(nsb_set_pattern(ctx, NSB_A10, P.a10.n_rows, P.a10.rowptr.data(), P.a10.colind.data()), "nsb_set_pattern(A10)");
+  check(nsb_set_pattern(ctx, NSB_S, P.s.n_rows, P.s.rowptr.data(), P.s.colind.data()), "nsb_set_pattern(S)");
+  check(nsb_set_quadrature(ctx, quad_rule), "nsb_set_quadrature");
+  check(nsb_set_force_faces(ctx, (int64_t)problem->ff.cell.size(), problem->ff.cell.data(), problem->ff.normal.data(),
+                            problem->ff.measure.data()),
+        "nsb_set_force_faces");
+  check(nsb_set_params(ctx, deltat, nu), "nsb_set_params");
+  check(nsb_set_solver(ctx, opt_rtol, opt_restart, opt_max_it, 0.5, NSB_PREC_ASIMPLE), "nsb_set_solver");
+  if (opt_sweeps_F > 0 && opt_sweeps_S > 0)
+    check(nsb_set_inner(ctx, opt_sweeps_F, 2.5 * opt_sweeps_F, opt_sweeps_S, 0.45 * opt_sweeps_S * opt_sweeps_S),
+          "nsb_set_inner");
+  check(nsb_finalize_setup(ctx), "nsb_finalize_setup");
+  if (pcout) {
+    std::cout << "\tInitializing the system right-hand side" << std::endl;
+    std::cout << "\tInitializing the solution vector" << std::endl;
+  }
+  solution.assign((size_t)d.n_u + d.n_p, 0.0);
+}
+
+void NavierStokes::set_solver_options(double gmres_rtol, int restart, int max_it, int sweeps_F, int sweeps_S) {
+  opt_rtol = gmres_rtol;
+  opt_restart = restart;
+  opt_max_it = max_it;
+  opt_sweeps_F = sweeps_F;
+  opt_sweeps_S = sweeps_S;
+  if (ctx) {
+    check(nsb_set_solver(ctx, opt_rtol, opt_restart, opt_max_it, 0.5, NSB_PREC_ASIMPLE), "nsb_set_solver");
+    if (sweeps_F > 0 && sweeps_S > 0)
+      check(nsb_set_inner(ctx, sweeps_F, 2.5 * sweeps_F, sweeps_S, 0.45 * sweeps_S * sweeps_S), "nsb_set_inner");
+  }
+}
+
+// reference :297-324: the dof set is fixed, the values follow the inlet's time
+void NavierStokes::refresh_dirichlet(double t) {
+  inlet_velocity.set_time(t);
+  const InletVelocity &inlet = inlet_velocity;
+  problem->bc = nsb::dirichlet_dofs(problem->mesh, problem->dofs, problem->bfaces, [&](const double *x, int c) {
+    Point<dim> p;
+    for (unsigned int r = 0; r < dim; ++r) p[r] = x[r];
+    return inlet.value(p, (unsigned int)c);
+  });
+  if (ctx)
+    check(nsb_set_dirichlet(ctx, (int64_t)problem->bc.dofs.size(), problem->bc.dofs.data(), problem->bc.values.data()),
+          "nsb_set_dirichlet");
+}
+
+// reference :133-330
+void NavierStokes::assemble(const double &t) {
+  forcing_term.set_time(t);
+  refresh_dirichlet(t);
+  check(nsb_set_params(ctx, deltat, nu), "nsb_set_params");
+  check(nsb_assemble(ctx, t), "nsb_assemble");
+}
+
+// reference :332-341
+void NavierStokes::set_re_number(int Re) {
+  const bool pcout = mpi_rank == 0;
+  if (pcout) std::cout << "-----------------------------------" << std::endl;
+  const double U = inlet_velocity.get_mean_vel();
+  nu = (U * Diameter) / Re;
+  if (pcout) {
+    std::cout << "New reynolds number setted to " << Re << " with nu = " << nu << " ." << std::endl;
+    std::cout << "-----------------------------------" << std::endl;
+  }
+}
+
+// reference :344-397
+void NavierStokes::solve_time_step(std::ostream &oss) {
+  int iters = 0;
+  double t_prec = 0, t_sol = 0;
+  check(nsb_solve_time_step(ctx, &iters, &t_prec, &t_sol), "nsb_solve_time_step");  // NSB_ENOCONV -> throws
+  last_iters = (unsigned int)iters;
+  if (mpi_rank == 0) {
+    std::cout << "  " << iters << " GMRES iterations" << std::endl;
+    std::cout << "Elapsed time for preconditioner initialisation: " << t_prec << " [s]" << std::endl;
+    std::cout << "Elapsed time for time step solution: " << t_sol << " [s]" << std::endl;
+    std::cout << std::endl;
+  }
+  oss << iters << "," << t_prec << "," << t_sol << ",";
+  check(nsb_get_solution(ctx, solution.data()), "nsb_get_solution");  // solution = solution_owned (:395)
+}
+
+// reference :831-929
+void NavierStokes::compute_forces(const double & /*time*/) {
+  if (mpi_rank == 0) std::cout << "Computing forces: " << std::endl;
+  double out[4];
+  check(nsb_compute_forces(ctx, inlet_velocity.get_mean_vel(), out), "nsb_compute_forces");
+  drag = out[0];
+  lift = out[1];
+  cd = out[2];
+  cl = out[3];
+  if (mpi_rank == 0) {
+    std::cout << "Drag coefficient (Cd): " << cd << "   Lift coefficient (Cl): " << cl << std::endl;
+    std::cout << "---------------------------------------------------" << std::endl;
+  }
+}
+
+// reference :439-499
+void NavierStokes::solve(unsigned int time_step) {
+  const bool pcout = mpi_rank == 0;
+  if (pcout) std::cout << "===================================================" << std::endl;
+  std::ofstream output_file("forces_vs_time.csv");
+  output_file << "time,deltat,GMRES_iters,time_prec_init,time_sol,Drag,Lift,Cd,Cl\n";
+  if (0 == time_step) {
+    time = 0.0;
+    if (pcout) std::cout << "Applying initial conditions" << std::endl;
+    std::fill(solution.begin(), solution.end(), 0.0);  // InitialConditions == 0
+  } else {
+    time = deltat * time_step;
+    if (pcout) std::cout << "Continuing execution from time step " << time_step << std::endl;
+    import_data(time_step);
+  }
+  check(nsb_set_solution(ctx, solution.data()), "nsb_set_solution");
+  export_data(time_step);
+  if (pcout) std::cout << "---------------------------------------------------" << std::endl;
+  while (time < T - 0.5 * deltat) {
+    time += deltat;
+    ++time_step;
+    if (pcout) std::cout << "n = " << std::setw(3) << time_step << ", t = " << std::setw(5) << time << ":" << std::flush;
+    assemble(time);
+    output_file << time << "," << deltat << ",";
+    solve_time_step(output_file);
+    compute_forces(time);
+    output_file << drag << "," << lift << "," << cd << "," << cl << "\n";
+    if (0 == time_step % step) {
+      output(time_step);
+      export_data(time_step);
+    }
+  }
+  output_file.close();
+}
+
+// reference :571-784.  With one process the rank-count-independent order is the
+// first-encounter order of the dofs when walking the cells by coarse-cell id
+// and each cell's dof_indices in FESystem order.
+void NavierStokes::compute_ordered_dofs_indices() {
+  const nsb::DofMap &d = problem->dofs;
+  const size_t N = (size_t)d.n_u + d.n_p;
+  renumbered_dofs.assign(N, 0);
+  std::vector<char> seen(N, 0);
+  unsigned int k = 0;
+  for (uint32_t dof : d.cell_dofs)
+    if (!seen[dof]) {
+      seen[dof] = 1;
+      renumbered_dofs[dof] = k++;
+    }
+}
+
+// reference :501-568: N raw doubles, position renumbered_dofs[i] holds dof i
+void NavierStokes::export_data(const unsigned int &time_step) {
+  if (renumbered_dofs.size() != solution.size()) compute_ordered_dofs_indices();
+  if (mpi_rank != 0) return;
+  std::vector<double> rbuf(solution.size());
+  for (size_t i = 0; i < solution.size(); ++i) rbuf[renumbered_dofs[i]] = solution[i];
+  const std::string file_name("../cache/state-ns-" + std::to_string(time_step) + ".dat");
+  std::ofstream f(file_name, std::fstream::binary);
+  f.write(reinterpret_cast<const char *>(rbuf.data()), (std::streamsize)(rbuf.size() * sizeof(double)));
+}
+
+// reference :787-805
+void NavierStokes::import_data(const unsigned int &time_step) {
+  if (renumbered_dofs.size() != solution.size()) compute_ordered_dofs_indices();
+  const std::string file_name("../cache/state-ns-" + std::to_string(time_step) + ".dat");
+  std::ifstream f(file_name, std::fstream::binary);
+  std::vector<double> inbuff(solution.size());
+  f.read(reinterpret_cast<char *>(inbuff.data()), (std::streamsize)(inbuff.size() * sizeof(double)));
+  if (!f) throw std::runtime_error("import_data: cannot read " + file_name);
+  for (size_t i = 0; i < solution.size(); ++i) solution[i] = inbuff[renumbered_dofs[i]];
+  if (ctx) check(nsb_set_solution(ctx, solution.data()), "nsb_set_solution");
+}
+
+// reference :808-828
+void NavierStokes::post_process(const unsigned int &initial_time_step, const unsigned int &final_time_step,
+                                const unsigned int &step_) {
+  const bool pcout = mpi_rank == 0;
+  if (pcout) std::cout << "=======================================================" << std::endl;
+  for (unsigned int s = initial_time_step; s <= final_time_step; s += step_) {
+    if (pcout) std::cout << "Importing time step " << s << " for post processing" << std::endl;
+    import_data(s);
+    compute_forces(s);
+    if (pcout) std::cout << "Exporting pvtu files for time step " << s << std::endl;
+    output(s);
+  }
+}
+
+// reference :400-436.  DataOut writes one patch per cell (vertices are not
+// shared between patches) with velocity / pressure / partitioning as point
+// data; the same layout is written here as ASCII VTU plus the .pvtu record.
+void NavierStokes::output(const unsigned int &time_step) const {
+  const nsb::Mesh &m = problem->mesh;
+  const nsb::DofMap &d = problem->dofs;
+  const int nv = dim + 1, NN = d.nn();
+  const size_t nc = m.n_cells();
+  const std::string base = "output-stokes_" + std::to_string(time_step);
+  const std::string piece = base + "." + std::to_string(mpi_rank) + ".vtu";
+  std::ofstream f("../output/" + piece);
+  if (!f) return;  // the reference's DataOut would throw; a missing ../output is not fatal for the solver
+  f << std::setprecision(9);
+  f << "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n"
+    << "<UnstructuredGrid>\n<Piece NumberOfPoints=\"" << nc * nv << "\" NumberOfCells=\"" << nc << "\">\n";
+  f << "<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+  for (size_t c = 0; c < nc; ++c)
+    for (int a = 0; a < nv; ++a) {
+      const double *p = &m.xyz[(size_t)m.cells[c * nv + a] * dim];
+      f << p[0] << " " << p[1] << " " << (dim == 3 ? p[2] : 0.0) << "\n";
+    }
+  f << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int32\" Name=\"connectivity\" format=\"ascii\">\n";
+  for (size_t i = 0; i < nc * nv; ++i) f << i << ((i + 1) % nv ? " " : "\n");
+  f << "</DataArray>\n<DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">\n";
+  for (size_t c = 1; c <= nc; ++c) f << c * nv << "\n";
+  f << "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n";
+  for (size_t c = 0; c < nc; ++c) f << (dim == 2 ? 5 : 10) << "\n";
+  f << "</DataArray>\n</Cells>\n<PointData Scalars=\"scalars\">\n";
+  f << "<DataArray type=\"Float64\" Name=\"velocity\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+  for (size_t c = 0; c < nc; ++c)
+    for (int a = 0; a < nv; ++a) {
+      const size_t node = d.cell_nodes[c * NN + a];
+      for (int k = 0; k < 3; ++k) f << (k < (int)dim ? solution[dim * node + k] : 0.0) << (k == 2 ? "\n" : " ");
+    }
+  f << "</DataArray>\n<DataArray type=\"Float64\" Name=\"pressure\" format=\"ascii\">\n";
+  for (size_t c = 0; c < nc; ++c)
+    for (int a = 0; a < nv; ++a) f << solution[(size_t)d.n_u + d.cell_pverts[c * nv + a]] << "\n";
+  f << "</DataArray>\n<DataArray type=\"Float64\" Name=\"partitioning\" format=\"ascii\">\n";
+  for (size_t c = 0; c < nc; ++c)
+    for (int a = 0; a < nv; ++a) f << (problem->part_cell.empty() ? 0 : problem->part_cell[c]) << "\n";
+  f << "</DataArray>\n</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n";
+  if (mpi_rank == 0) {
+    std::ofstream pv("../output/" + base + ".pvtu");
+    pv << "<?xml version=\"1.0\"?>\n<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n"
+       << "<PUnstructuredGrid GhostLevel=\"0\">\n<PPointData Scalars=\"scalars\">\n"
+       << "<PDataArray type=\"Float64\" Name=\"velocity\" NumberOfComponents=\"3\" format=\"ascii\"/>\n"
+       << "<PDataArray type=\"Float64\" Name=\"pressure\" format=\"ascii\"/>\n"
+       << "<PDataArray type=\"Float64\" Name=\"partitioning\" format=\"ascii\"/>\n</PPointData>\n"
+       << "<PPoints>\n<PDataArray type=\"Float64\" NumberOfComponents=\"3\"/>\n</PPoints>\n";
+    for (unsigned int r = 0; r < mpi_size; ++r) pv << "<Piece Source=\"" << base << "." << r << ".vtu\"/>\n";
+    pv << "</PUnstructuredGrid>\n</VTKFile>\n";
+  }
+}

@@ -1,0 +1,89 @@
+"""The C++ NavierStokes facade (host/NavierStokes.hpp) and its driver mains."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, PKG_NAME
+
+PKG_DIR = os.path.join(ROOT, PKG_NAME)
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("case,dim", [("2D/test_01", 2), ("2D/test_02", 2), ("2D/test_03", 2), ("2D/test_naca", 2),
+                                      ("3D/test_01", 3), ("3D/test_02", 3), ("3D/test_03", 3)])
+def test_reference_drivers_compile_unmodified_against_facade(pkg, tmp_path, case, dim):
+    """Drop-in check: the reference's own driver sources (compiled where they
+    lie, never copied) build against this repo's NavierStokes.hpp."""
+    subprocess.check_call(["make", "-C", ROOT, "host", "cuda"], stdout=subprocess.DEVNULL)
+    src = glob.glob(os.path.join(REF, "tests", case, "src", "*.cpp"))
+    assert len(src) == 1
+    out = str(tmp_path / "drv")
+    cmd = ["/usr/bin/g++", "-O0", "-std=c++17", "-fopenmp", f"-DDIM={dim}", "-I" + os.path.join(PKG_DIR, "host"),
+           "-I" + os.path.join(ROOT, "include"), "-o", out, src[0], os.path.join(PKG_DIR, "host", "NavierStokes.cpp"),
+           "-L" + PKG_DIR, "-lnsb_host", "-lnsb", "-Wl,-rpath," + PKG_DIR]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def _run_driver(tmp_path, binary, mesh_name, h, T):
+    subprocess.check_call(["make", "-C", ROOT, "drivers"], stdout=subprocess.DEVNULL)
+    for d in ("build", "output", "cache", "mesh"):
+        os.makedirs(tmp_path / d, exist_ok=True)
+    msh = str(tmp_path / "mesh" / "domain.msh")
+    subprocess.check_call([os.path.join(PKG_DIR, "drivers", "make_mesh"), mesh_name, str(h), msh])
+    r = subprocess.run([os.path.join(PKG_DIR, "drivers", binary), "../mesh/domain.msh", str(T)],
+                       cwd=str(tmp_path / "build"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return msh, r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("binary,mesh_name,h,dim,um", [("d2_test_01", "2d-cylinder", 0.05, 2, 0.3),
+                                                       ("d3_test_01", "3d-cylinder", 0.1, 3, 0.45)])
+def test_driver_time_loop_matches_oracle(pkg, oracle_mod, tmp_path, binary, mesh_name, h, dim, um):
+    """ctor -> set_re_number -> setup -> compute_ordered_dofs_indices -> solve
+    (reference tests/3D/test_01/src/test_01.cpp:57-61) on a generated .msh;
+    forces_vs_time.csv against the oracle stepping the same mesh file."""
+    nsteps = 4
+    msh, stdout = _run_driver(tmp_path, binary, mesh_name, h, nsteps * 0.01)
+    assert "GMRES iterations" in stdout and "Drag coefficient (Cd):" in stdout
+    lines = open(tmp_path / "build" / "forces_vs_time.csv").read().strip().split("\n")
+    assert lines[0] == "time,deltat,GMRES_iters,time_prec_init,time_sol,Drag,Lift,Cd,Cl"
+    rows = np.array([[float(x) for x in l.split(",")] for l in lines[1:]])
+    assert rows.shape == (nsteps, 9)
+    assert np.allclose(rows[:, 0], 0.01 * np.arange(1, nsteps + 1)) and (rows[:, 2] > 0).all()
+    prob = pkg.Problem.read_msh(msh, dim).build(inlet=(0, um, 0.41, 0))
+    orc = oracle_mod.Oracle(dim, prob.array("xyz"), prob.array("cells"), prob.array("bfaces"), prob.array("bids"))
+    orc.set_inlet(0, um, 0.41, 0)
+    orc.set_params(0.01, 1e-3)
+    orc.set_re_number(20)
+    orc.set_solver(1e-10, 30, 10000, 1e-8)
+    t = 0.0
+    for n in range(nsteps):
+        t += 0.01
+        orc.assemble(t)
+        orc.solve_time_step()
+        f = orc.compute_forces(t)
+        # both solvers stop at their own 1e-6 / 1e-10 tolerance: compare to 1e-3 relative
+        assert abs(rows[n, 7] - f[2]) < 2e-3 * abs(f[2]), (n, rows[n], f)
+    # checkpoint files: N raw doubles (reference NavierStokes.cpp:560-567); step 0 holds the zero initial state
+    st0 = np.fromfile(tmp_path / "cache" / "state-ns-0.dat")
+    assert st0.size == orc.N and not st0.any()
+
+
+@pytest.mark.gpu
+def test_checkpoint_and_vtu_output(pkg, tmp_path):
+    msh, _ = _run_driver(tmp_path, "d2_test_02", "2d-cylinder", 0.06, 0.08)  # dt 0.02, output step 2
+    out = sorted(os.listdir(tmp_path / "output"))
+    assert "output-stokes_2.0.vtu" in out and "output-stokes_2.pvtu" in out and "output-stokes_4.pvtu" in out
+    prob = pkg.Problem.read_msh(msh, 2).build()
+    s = prob.sizes()
+    N = s["n_u"] + s["n_p"]
+    st = np.fromfile(tmp_path / "cache" / "state-ns-4.dat")
+    assert st.size == N and np.isfinite(st).all() and np.abs(st).max() > 0.1
+    txt = open(tmp_path / "output" / "output-stokes_4.0.vtu").read()
+    assert f'NumberOfCells="{s["n_cells"]}"' in txt and 'Name="velocity"' in txt and 'Name="partitioning"' in txt
