@@ -43,8 +43,11 @@ def parse():
                     help="target edge length of the mesh (0.011 ~ 10M DoFs)")
     ap.add_argument("--cpu-h", type=float, default=0.05, help="mesh of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--canonical-spmv", action="store_true",
+                    help="also time y = A x on the materialised canonical (reference) CSR")
     ap.add_argument("--alpha", type=float, default=0.5)
-    ap.add_argument("--sweeps", type=str, default="4,10,20,300", help="kF,ratioF,kS,ratioS of the inner sweeps")
+    ap.add_argument("--sweeps", type=str, default="0,0,0,0",
+                    help="kF,ratioF,kS,ratioS of the inner sweeps (0 = automatic)")
     return ap.parse_args()
 
 
@@ -104,19 +107,33 @@ class ClockSampler:
         return out
 
 
-def spmv_bytes(info):
-    """Algorithmic bytes of y = A x on the canonical block CSR:
-    12 B per non-zero, 8 B row offset per row, y written and x read once."""
+def spmv_canonical_bytes(info):
+    """Algorithmic bytes of y = A x on the canonical (reference) block CSR
+    (DESIGN.md §5): 12 B per stored non-zero, 8 B row offset per row, y written
+    and x read once."""
     n_u, n_p = info["n_u"], info["n_p"]
     nnz = info["nnz_a00"] + info["nnz_a01"] + info["nnz_a10"]
-    return 12 * nnz + 8 * (2 * n_u + n_p + 3) + 8 * (n_u + n_p) + 8 * (n_u + n_p)
+    return 12 * nnz + 8 * (2 * n_u + n_p + 3) + 16 * (n_u + n_p)
 
 
-def sweep_bytes(info):
-    """One Chebyshev-Jacobi sweep on F = A00: matrix stream + z gathered once
-    + b, dinv, d (read), z_i (read), d, znew (written)."""
+def spmv_bytes(info, dim=3):
+    """Same product on the storage the solver uses: A00 = F_s (x) I_dim kept as
+    the node-level scalar CSR F_s (nnz_a00 / dim^2 non-zeros)."""
+    n_u, n_p = info["n_u"], info["n_p"]
+    nnz = info["nnz_a00"] // (dim * dim) + info["nnz_a01"] + info["nnz_a10"]
+    return 12 * nnz + 8 * (n_u // dim + n_u + n_p + 3) + 16 * (n_u + n_p)
+
+
+def sweep_bytes(info, dim=3):
+    """One Chebyshev-Jacobi sweep on F: F_s stream + z gathered once + b, dinv,
+    d, z_i read and d, znew written."""
     n_u = info["n_u"]
-    return 12 * info["nnz_a00"] + 8 * (n_u + 1) + 8 * n_u * 7
+    return 12 * (info["nnz_a00"] // (dim * dim)) + 8 * (n_u // dim + 1) + 8 * n_u * 7
+
+
+def sweep_s_bytes(info):
+    n_p = info["n_p"]
+    return 12 * info["nnz_s"] + 8 * (n_p + 1) + 8 * n_p * 7
 
 
 def assembly_bytes(info, dim=3):
@@ -124,7 +141,7 @@ def assembly_bytes(info, dim=3):
     written once, dof ids + slots + vertex coordinates per cell, velocity read, rhs written."""
     nn, nv = (10, 4) if dim == 3 else (6, 3)
     per_cell = 4 * (nn + nv) + 4 * nv + 2 * (nn * nn + 2 * nn * nv)
-    nnz = info["nnz_a00"] + info["nnz_a01"] + info["nnz_a10"]
+    nnz = info["nnz_a00"] // (dim * dim) + info["nnz_a01"] + info["nnz_a10"]
     return 8 * nnz + info["n_cells"] * per_cell + 8 * info["n_u"] + 8 * (info["n_u"] + info["n_p"])
 
 
@@ -164,7 +181,7 @@ def main():
     config = {"workload": f"{a.mesh} Re=20 (mesh/domain3D2.geo geometry, tests/3D/test_01 parameters), h={a.h}",
               "mesh": a.mesh, "h": a.h, "deltat": DT, "Re": RE, "quadrature": "dealii95 (14-pt)",
               "gmres": "left-preconditioned GMRES(28), rtol 1e-6 (reference stopping rule)",
-              "preconditioner": f"aSIMPLE alpha={a.alpha}, Chebyshev-Jacobi sweeps F:{kF} S:{kS}",
+              "preconditioner": f"aSIMPLE alpha={a.alpha}, Chebyshev-Jacobi sweeps F:{kF} S:{kS} (0 = automatic)",
               "l2_policy": "inputs larger than L2 (matrix >> 126 MB)", "parallelism": f"dd{a.gpus}"}
 
     if a.impl == "reference":
@@ -202,7 +219,7 @@ def main():
     nu = prob.mean_velocity(0.0) * 0.4 / RE  # set_re_number, reference :332-341
     dev.set_params(DT, nu)
     dev.set_solver(1e-6, 28, 10000, a.alpha)
-    dev.set_inner(int(kF), float(rF), int(kS), float(rS))
+    dev.set_inner(int(kF), float(rF) if int(kF) > 0 else 0.0, int(kS), float(rS) if int(kS) > 0 else 0.0)
     info = dev.info()
     N = info["n_u"] + info["n_p"]
     t_setup = time.perf_counter() - t_setup
@@ -255,20 +272,34 @@ def main():
     ms_e2e = 1e3 * (time.perf_counter() - t0) / a.steps
     # kernel micro-benchmarks on the resident system (CUDA events on the ctx stream)
     reps = 20
-    ms_spmv = dev.bench_kernel(0, reps)
+    ms_spmv = dev.bench_kernel(5, reps)
     ms_sweep = dev.bench_kernel(4, reps)
+    ms_sweep_s = dev.bench_kernel(6, reps)
     ms_asm = dev.bench_kernel(1, 5)
     ms_prec = dev.bench_kernel(2, 5)
+    ms_schur = dev.bench_kernel(3, 5)
+    ms_spmv_can = dev.bench_kernel(0, reps) if a.canonical_spmv else None
     clocks = sampler.stop()
 
     gb = 1e-9
-    spmv_gbs = spmv_bytes(info) * gb / (ms_spmv * 1e-3)
-    sweep_gbs = sweep_bytes(info) * gb / (ms_sweep * 1e-3)
+    spmv_gbs = spmv_bytes(info, dim) * gb / (ms_spmv * 1e-3)
+    sweep_gbs = sweep_bytes(info, dim) * gb / (ms_sweep * 1e-3)
+    sweep_s_gbs = sweep_s_bytes(info) * gb / (ms_sweep_s * 1e-3)
     asm_gbs = assembly_bytes(info, dim) * gb / (ms_asm * 1e-3)
-    roof = {"bound": "hbm", "kernel": "cheb_sweep_kernel<16> on A00 (Jacobi-type inner sweep, SpMV-fused)",
-            "achieved": sweep_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sweep_gbs / hbm_peak,
-            "traffic": None, "peak_source": peak_src, "ms_per_launch": ms_sweep,
-            "algorithmic_bytes_per_launch": sweep_bytes(info)}
+    # share of one outer GMRES iteration: (kF-1) F sweeps, (kS-1) S sweeps, one block product
+    kF_eff = int(kF) if int(kF) > 0 else 3
+    kS_eff = int(kS) if int(kS) > 0 else max(4, round(1.5 * (max(30.0, 1.7 * info["n_p"] ** (2.0 / 3))) ** 0.5))
+    shares = {"fs_cheb_sweep_kernel (Jacobi-type sweep on F, node-block CSR)": ((kF_eff - 1) * ms_sweep, sweep_gbs,
+                                                                               sweep_bytes(info, dim), ms_sweep),
+              "cheb_sweep_kernel (Jacobi-type sweep on S)": ((kS_eff - 1) * ms_sweep_s, sweep_s_gbs,
+                                                             sweep_s_bytes(info), ms_sweep_s),
+              "fs_apply_kernel + spmv_kernel (block product y = A x)": (ms_spmv, spmv_gbs, spmv_bytes(info, dim),
+                                                                       ms_spmv)}
+    top = max(shares, key=lambda k: shares[k][0])
+    roof = {"bound": "hbm", "kernel": top, "achieved": shares[top][1], "peak": hbm_peak, "unit": "GB/s",
+            "frac": shares[top][1] / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "ms_per_launch": shares[top][3], "algorithmic_bytes_per_launch": shares[top][2],
+            "ms_per_gmres_iteration_by_kernel": {k: v[0] for k, v in shares.items()}}
     line = {"metric": "time_per_step", "value": ms_dev, "unit": "ms/step", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -276,6 +307,10 @@ def main():
             "phase_ms": {"assemble": dev_stats["asm"], "prec_init": dev_stats["prec"], "solve": dev_stats["sol"]},
             "assembly_dofs_per_s": N / (ms_asm * 1e-3), "assembly_gbs": asm_gbs, "assembly_ms": ms_asm,
             "spmv_gbs": spmv_gbs, "spmv_frac_of_hbm": spmv_gbs / hbm_peak, "spmv_ms": ms_spmv,
+            "sweep_F_gbs": sweep_gbs, "sweep_F_ms": ms_sweep, "sweep_S_gbs": sweep_s_gbs, "sweep_S_ms": ms_sweep_s,
+            "schur_ms": ms_schur,
+            "spmv_canonical_gbs": (spmv_canonical_bytes(info) * gb / (ms_spmv_can * 1e-3)) if ms_spmv_can else None,
+            "spmv_canonical_ms": ms_spmv_can,
             "prec_apply_ms": ms_prec, "cd": float(forces[2]), "cl": float(forces[3]),
             "setup_s": t_setup, "device_bytes": info["device_bytes"],
             "roofline": roof, "clocks": clocks,

@@ -84,7 +84,8 @@ int nsb_set_solver(nsb_ctx *ctx, double gmres_rtol, int restart, int max_it, dou
 /* Inner solves of aSIMPLE: fixed-degree Chebyshev-Jacobi polynomials in place
  * of the reference's ILU-preconditioned GMRES to 1e-2 (north star: Jacobi-type
  * inner sweeps).  sweeps = polynomial degree; eig_ratio = assumed
- * lambda_max/lambda_min of D^-1 M targeted by the polynomial. */
+ * lambda_max/lambda_min of D^-1 M targeted by the polynomial.  sweeps <= 0
+ * (the default) selects an automatic choice from the problem size. */
 int nsb_set_inner(nsb_ctx *ctx, int sweeps_F, double eig_ratio_F, int sweeps_S, double eig_ratio_S);
 
 /* ---- state ------------------------------------------------------------ */
@@ -112,8 +113,11 @@ int nsb_get_rhs(nsb_ctx *ctx, double *rhs_host);
 int nsb_vmult(nsb_ctx *ctx, const double *x_host, double *y_host);
 /* Device-resident micro-benchmarks: run `reps` launches and return the mean
  * kernel time in milliseconds measured with CUDA events on the ctx stream.
- * which: 0 block SpMV y=Ax (canonical CSR), 1 assembly (zero+cell loop+BC),
- * 2 preconditioner apply, 3 S = B Di Bt, 4 Chebyshev sweep on F. */
+ * which: 0 block SpMV y=Ax on the canonical (reference) CSR, 1 assembly
+ * (zero + cell loop + Dirichlet rows), 2 preconditioner apply, 3 S = B Di Bt,
+ * 4 Chebyshev sweep on F (node-block storage), 5 block SpMV on the compressed
+ * storage the solver uses, 6 Chebyshev sweep on S.  Add 0x100 to flush L2
+ * between repetitions. */
 int nsb_bench_kernel(nsb_ctx *ctx, int which, int reps, double *ms_mean);
 /* Launch counter of this context's own kernels (for bench.py gpu_launches). */
 int64_t nsb_launch_count(const nsb_ctx *ctx);

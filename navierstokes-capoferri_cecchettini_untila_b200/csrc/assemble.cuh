@@ -10,9 +10,13 @@
 //                 replicated on the dim diagonal component positions of A00,
 //   Bt(a,c;k) = -|J| sum_d Jinv[d][c] D^(a,k,d)   -> A01 and (transposed) A10,
 //   rhs(a,c)  = |J|/dt sum_n M^(a,n) U_n[c].
-// Values are scatter-added with red.global.add.f64 into the precomputed CSR
-// positions: per cell 16-bit "slots" (rank of the column node inside the row
-// node's adjacency list) address all dim component copies at once.
+// A00 = F_s (x) I_dim exactly (also after the Dirichlet rows, which hit all
+// components of a node alike), so only the scalar node-level matrix F_s is
+// stored and assembled: dim^2 times fewer bytes than the canonical block the
+// reference keeps; the canonical values are materialised on request
+// (nsb_get_matrix_values).  Values are scatter-added with red.global.add.f64
+// into precomputed CSR positions: per cell 16-bit "slots" = rank of the column
+// node inside the row node's adjacency list.
 #pragma once
 #include "common.cuh"
 
@@ -27,8 +31,8 @@ struct AsmArgs {
   const uint16_t *slot00;       // n_cells*NN*NN
   const uint16_t *slot01;       // n_cells*NN*NV
   const uint16_t *slot10;       // n_cells*NV*NN
-  const int64_t *rowptr00, *rowptr01, *rowptr10;
-  double *val00, *val01, *val10;
+  const int64_t *nptr, *rowptr01, *rowptr10;  // nptr: node-level row offsets of F_s
+  double *fs_val, *val01, *val10;
   double *rhs;
   const double *sol;  // previous-step solution (velocity part is read)
   const FeTables *fe;
@@ -54,7 +58,7 @@ __device__ __forceinline__ int64_t find_col(const uint32_t *colind, int64_t b, i
 
 template <int DIM>
 __global__ void build_slots_kernel(int64_t n_cells, const uint32_t *__restrict__ cell_nodes,
-                                   const uint32_t *__restrict__ cell_pverts, CsrView a00, CsrView a01, CsrView a10,
+                                   const uint32_t *__restrict__ cell_pverts, CsrView fs, CsrView a01, CsrView a10,
                                    uint16_t *slot00, uint16_t *slot01, uint16_t *slot10, int *err) {
   constexpr int NV = DIM + 1, NN = DIM == 2 ? 6 : 10, PER = NN * NN + 2 * NN * NV;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,13 +68,10 @@ __global__ void build_slots_kernel(int64_t n_cells, const uint32_t *__restrict__
   const uint32_t *nodes = cell_nodes + cell * NN, *pv = cell_pverts + cell * NV;
   if (e < NN * NN) {
     const int a = e / NN, b = e % NN;
-    const int64_t row = (int64_t)DIM * nodes[a], rb = a00.rowptr[row], re = a00.rowptr[row + 1];
-    const int64_t pos = find_col(a00.colind, rb, re, DIM * nodes[b]);
-    const int64_t k = (pos - rb) / DIM;
-    if (pos < 0 || (re - rb) % DIM != 0 || (pos - rb) % DIM != 0 || k > 65535 ||
-        a00.rowptr[row + 2] - a00.rowptr[row + 1] != re - rb)
-      atomicExch(err, 1);
-    slot00[cell * NN * NN + e] = (uint16_t)k;
+    const int64_t row = nodes[a], rb = fs.rowptr[row], re = fs.rowptr[row + 1];
+    const int64_t pos = find_col(fs.colind, rb, re, nodes[b]);
+    if (pos < 0 || pos - rb > 65535) atomicExch(err, 1);
+    slot00[cell * NN * NN + e] = (uint16_t)(pos - rb);
     return;
   }
   e -= NN * NN;
@@ -93,7 +94,7 @@ __global__ void build_slots_kernel(int64_t n_cells, const uint32_t *__restrict__
   }
 }
 
-__global__ void diag_positions_kernel(CsrView A, int64_t *diagpos, int *err) {
+__global__ void diag_positions_kernel(CsrView A, int64_t *diagpos, int *err) {  // A: F_s (node level) or S
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n_rows) return;
   const int64_t pos = find_col(A.colind, A.rowptr[i], A.rowptr[i + 1], (uint32_t)i);
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs 
   __shared__ double s_U[kAsmWarps][NN][DIM];
   __shared__ double s_uq[kAsmWarps][NQ][DIM];
   __shared__ int64_t s_rp00[kAsmWarps][NN], s_rp01[kAsmWarps][NN], s_rp10[kAsmWarps][NV];
-  __shared__ int s_len00[kAsmWarps][NN], s_len01[kAsmWarps][NN];
+  __shared__ int s_len01[kAsmWarps][NN];
   __shared__ uint32_t s_node[kAsmWarps][NN];
 
   for (int i = threadIdx.x; i < NQ; i += blockDim.x) s_w[i] = A.fe->w[i];
@@ -218,9 +219,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs 
     if (lane < NN) {
       const uint32_t node = __ldg(A.cell_nodes + cell * NN + lane);
       s_node[warp][lane] = node;
-      const int64_t r0 = __ldg(A.rowptr00 + (int64_t)DIM * node), r1 = __ldg(A.rowptr00 + (int64_t)DIM * node + 1);
-      s_rp00[warp][lane] = r0;
-      s_len00[warp][lane] = (int)(r1 - r0);
+      s_rp00[warp][lane] = __ldg(A.nptr + node);
       const int64_t q0 = __ldg(A.rowptr01 + (int64_t)DIM * node), q1 = __ldg(A.rowptr01 + (int64_t)DIM * node + 1);
       s_rp01[warp][lane] = q0;
       s_len01[warp][lane] = (int)(q1 - q0);
@@ -255,7 +254,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs 
     }
     __syncwarp();
 
-    // ---- scalar velocity block -> A00 (dim copies) ----
+    // ---- scalar velocity block -> F_s ----
     const uint16_t *sl00 = A.slot00 + cell * (NN * NN);
     for (int p = lane; p < NN * NN; p += 32) {
       const int a = p / NN, b = p % NN;
@@ -272,10 +271,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs 
         acc += s_w[q] * (A.nu * gg + s_phi[q][a] * ug);
       }
       const double v = adet * (acc + s_mhat[a][b] * A.inv_dt);
-      const int64_t base = s_rp00[warp][a] + (int64_t)DIM * sl00[p];
-      const int len = s_len00[warp][a];
-#pragma unroll
-      for (int c = 0; c < DIM; ++c) atomicAdd(A.val00 + base + (int64_t)c * len + c, v);
+      atomicAdd(A.fs_val + s_rp00[warp][a] + sl00[p], v);
     }
     // ---- pressure-velocity coupling -> A01 and A10 (reference :222-229) ----
     const uint16_t *sl01 = A.slot01 + cell * (NN * NV), *sl10 = A.slot10 + cell * (NV * NN);
@@ -304,14 +300,14 @@ __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs 
 // Dirichlet rows (MatrixTools::apply_boundary_values, eliminate_columns=false,
 // reference :326-328).  One warp per constrained dof.
 // ---------------------------------------------------------------------------
-__global__ void first_diag_kernel(const double *__restrict__ val00, const int64_t *__restrict__ diagpos, int64_t n_u,
-                                  double *first_diag) {
+__global__ void first_diag_kernel(const double *__restrict__ fs_val, const int64_t *__restrict__ diagpos,
+                                  int64_t n_nodes, double *first_diag) {
   // "first non-zero diagonal entry in the local range": a serial scan that in
   // practice stops at row 0.
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     double d = 1.0;
-    for (int64_t i = 0; i < n_u; ++i) {
-      const double v = val00[diagpos[i]];
+    for (int64_t i = 0; i < n_nodes; ++i) {
+      const double v = fs_val[diagpos[i]];
       if (v != 0.0) {
         d = fabs(v);
         break;
@@ -321,25 +317,64 @@ __global__ void first_diag_kernel(const double *__restrict__ val00, const int64_
   }
 }
 
-__global__ void apply_dirichlet_kernel(int64_t n_bc, const uint32_t *__restrict__ dofs,
-                                       const double *__restrict__ vals, double factor, CsrView a00, CsrView a01,
+// bc_nodes: constrained nodes (all dim components of a node are constrained
+// together in the reference, :300-324); vals: dim values per node.
+template <int DIM>
+__global__ void apply_dirichlet_kernel(int64_t n_bc_nodes, const uint32_t *__restrict__ bc_nodes,
+                                       const double *__restrict__ vals, double factor, CsrView fs, CsrView a01,
                                        const int64_t *__restrict__ diagpos, const double *__restrict__ first_diag,
                                        int mode, double *rhs, double *sol) {
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (w >= n_bc) return;
-  const uint32_t i = dofs[w];
-  const int64_t dp = diagpos[i];
-  double dg = a00.val[dp];
+  if (w >= n_bc_nodes) return;
+  const uint32_t A = bc_nodes[w];
+  const int64_t dp = diagpos[A];
+  double dg = fs.val[dp];
   __syncwarp();
   if (mode == NSB_BCDIAG_FIRST || dg == 0.0) dg = *first_diag;
-  for (int64_t k = a00.rowptr[i] + lane; k < a00.rowptr[i + 1]; k += 32) a00.val[k] = (k == dp) ? dg : 0.0;
-  for (int64_t k = a01.rowptr[i] + lane; k < a01.rowptr[i + 1]; k += 32) a01.val[k] = 0.0;
-  if (lane == 0) {
-    const double g = vals[w] * factor;
-    rhs[i] = g * dg;
-    sol[i] = g;
+  for (int64_t k = fs.rowptr[A] + lane; k < fs.rowptr[A + 1]; k += 32) fs.val[k] = (k == dp) ? dg : 0.0;
+  for (int64_t k = a01.rowptr[(int64_t)DIM * A] + lane; k < a01.rowptr[(int64_t)DIM * A + DIM]; k += 32)
+    a01.val[k] = 0.0;
+  if (lane < DIM) {
+    const double g = vals[w * DIM + lane] * factor;
+    rhs[(int64_t)DIM * A + lane] = g * dg;
+    sol[(int64_t)DIM * A + lane] = g;
   }
+}
+
+// canonical A00 values from F_s: val[rowptr(dim*A+c) + dim*k + c'] = (c == c') F_s[A,k]
+template <int DIM>
+__global__ void expand_values_kernel(int64_t n_nodes, const int64_t *__restrict__ nptr,
+                                     const double *__restrict__ fs_val, double *__restrict__ val00) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_nodes) return;
+  const int64_t b = nptr[w], len = nptr[w + 1] - b;
+  for (int c = 0; c < DIM; ++c) {
+    double *o = val00 + DIM * DIM * b + c * DIM * len;
+    for (int64_t k = lane; k < DIM * len; k += 32) o[k] = (k % DIM == c) ? fs_val[b + k / DIM] : 0.0;
+  }
+}
+
+// node-level adjacency from a canonical A00 pattern (and structure check)
+template <int DIM>
+__global__ void compress_pattern_kernel(int64_t n_nodes, const int64_t *__restrict__ rowptr,
+                                        const uint32_t *__restrict__ colind, int64_t *nptr, uint32_t *ncol, int *err) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_nodes) return;
+  const int64_t rb = rowptr[DIM * w], len = (rowptr[DIM * w + 1] - rb) / DIM;
+  bool bad = rb % (DIM * DIM) != 0 || (rowptr[DIM * w + 1] - rb) % DIM != 0;
+  for (int c = 1; c < DIM; ++c) bad |= rowptr[DIM * w + c + 1] - rowptr[DIM * w + c] != DIM * len;
+  if (lane == 0) nptr[w] = rb / (DIM * DIM);
+  if (w == n_nodes - 1 && lane == 0) nptr[n_nodes] = rowptr[DIM * n_nodes] / (DIM * DIM);
+  for (int64_t k = lane; k < len; k += 32) {
+    const uint32_t c0 = colind[rb + DIM * k];
+    bad |= c0 % DIM != 0;
+    for (int c = 1; c < DIM; ++c) bad |= colind[rb + DIM * k + c] != c0 + c;
+    if (!bad) ncol[rb / (DIM * DIM) + k] = c0 / DIM;
+  }
+  if (bad) atomicExch(err, 6);
 }
 
 }  // namespace nsb

@@ -34,18 +34,20 @@ struct nsb_ctx {
   // immutable inputs
   DevBuf<double> xyz;
   DevBuf<uint32_t> cell_verts, cell_nodes, cell_pverts;
-  CsrDev a00, a01, a10, s;
+  CsrDev fs;             // F_s: node-level scalar velocity block, A00 = F_s (x) I_dim
+  CsrDev a00;            // canonical A00, materialised lazily for the parity taps / canonical SpMV bench
+  CsrDev a01, a10, s;
   std::vector<int64_t> h_rp01, h_rp10;  // kept until finalize for the symbolic S = A10*A01
   std::vector<uint32_t> h_ci01, h_ci10;
   DevBuf<uint16_t> slot00, slot01, slot10;
-  DevBuf<int64_t> diag00, diagS;
+  DevBuf<int64_t> diagF, diagS;
   DevBuf<FeTables> fe;
   DevBuf<int> errflag;
   // system vectors
   DevBuf<double> rhs, sol, di, dis, first_diag;
   // boundary data
-  DevBuf<uint32_t> bc_dofs;
-  DevBuf<double> bc_vals;
+  DevBuf<uint32_t> bc_nodes;  // constrained nodes (all dim components), ascending
+  DevBuf<double> bc_vals;     // dim values per constrained node
   double bc_factor = 1.0;
   int bc_mode = NSB_BCDIAG_KEEP;
   DevBuf<uint32_t> ff_cell;
@@ -53,8 +55,8 @@ struct nsb_ctx {
   // parameters (NavierStokes.hpp:254-256, 306; NavierStokes.cpp:348, 972-973)
   double dt = 0.01, nu = 1e-3, alpha = 0.5, rtol = 1e-6;
   int restart = 28, max_it = 10000, prec = NSB_PREC_ASIMPLE;
-  int sweepsF = 4, sweepsS = 20;
-  double ratioF = 10.0, ratioS = 300.0;
+  int sweepsF = 0, sweepsS = 0;  // 0 = automatic (see auto_inner)
+  double ratioF = 0.0, ratioS = 0.0;
   // Krylov work space
   DevBuf<double> V, tmpN, hdev, partials, coef;
   DevBuf<unsigned> counter;
@@ -107,6 +109,8 @@ inline unsigned blocks_for(int64_t n_threads, int block = 256) { return (unsigne
     NSB_CUDA(cudaGetLastError());                                \
   } while (0)
 
+void fs_apply(nsb_ctx *c, int mode, bool with_a01, const double *xu, const double *xp, const double *d, double *y);
+
 int pick_L(const CsrDev &A) {
   const double mean = A.n_rows ? (double)A.nnz / (double)A.n_rows : 0.0;
   return mean < 12 ? 4 : mean < 40 ? 8 : mean < 120 ? 16 : 32;
@@ -128,7 +132,14 @@ void spmv(nsb_ctx *c, const CsrDev &A, int mode, const double *x, const double *
 #undef NSB_SPMV_CASE
 }
 
+// y = A x on the compressed storage: velocity rows F_s (+A01), pressure rows A10
 void block_spmv(nsb_ctx *c, const double *x, double *y) {
+  fs_apply(c, 0, true, x, x + c->n_u, nullptr, y);
+  spmv(c, c->a10, 0, x, nullptr, nullptr, y + c->n_u);
+}
+
+// same product on the canonical (reference) block CSR; needs the materialised A00
+void block_spmv_canonical(nsb_ctx *c, const double *x, double *y) {
   const int L = c->spmv_L;
   const unsigned grid = blocks_for(c->N * L);
   if (L == 4) NSB_LAUNCH(c, block_spmv_kernel<4>, grid, 256, c->a00.view(), c->a01.view(), c->a10.view(), x, y);
@@ -147,18 +158,60 @@ void cheb_sweep(nsb_ctx *c, const CsrDev &M, const double *dinv, const double *b
   if (L == 32) NSB_LAUNCH(c, cheb_sweep_kernel<32>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
 }
 
+int pick_L_nodes(const CsrDev &F) {
+  const double mean = F.n_rows ? (double)F.nnz / (double)F.n_rows : 0.0;
+  return mean < 12 ? 4 : mean < 48 ? 8 : 16;
+}
+
+// y_u = F x_u (+ A01 x_p)  [mode 0]  or  y = d .* (F x_u)  [mode 3]
+void fs_apply(nsb_ctx *c, int mode, bool with_a01, const double *xu, const double *xp, const double *d, double *y) {
+  const int L = pick_L_nodes(c->fs);
+  const unsigned grid = blocks_for(c->fs.n_rows * L);
+  CsrView a01 = c->a01.view();
+  if (!with_a01) a01.rowptr = nullptr;
+#define NSB_FS_CASE(DD, LL, MM) \
+  if (c->dim == DD && L == LL && mode == MM) NSB_LAUNCH(c, (fs_apply_kernel<DD, LL, MM>), grid, 256, c->fs.view(), a01, xu, xp, d, y)
+#define NSB_FS_L(DD, LL) NSB_FS_CASE(DD, LL, 0); NSB_FS_CASE(DD, LL, 3)
+  NSB_FS_L(2, 4);
+  NSB_FS_L(2, 8);
+  NSB_FS_L(2, 16);
+  NSB_FS_L(3, 4);
+  NSB_FS_L(3, 8);
+  NSB_FS_L(3, 16);
+#undef NSB_FS_L
+#undef NSB_FS_CASE
+}
+
+void fs_cheb_sweep(nsb_ctx *c, const double *dinv, const double *b, const double *z, double *d, double *znew,
+                   double c1, double c2) {
+  const int L = pick_L_nodes(c->fs);
+  const unsigned grid = blocks_for(c->fs.n_rows * L);
+#define NSB_FC_CASE(DD, LL) \
+  if (c->dim == DD && L == LL) NSB_LAUNCH(c, (fs_cheb_sweep_kernel<DD, LL>), grid, 256, c->fs.view(), dinv, b, z, d, znew, c1, c2)
+  NSB_FC_CASE(2, 4);
+  NSB_FC_CASE(2, 8);
+  NSB_FC_CASE(2, 16);
+  NSB_FC_CASE(3, 4);
+  NSB_FC_CASE(3, 8);
+  NSB_FC_CASE(3, 16);
+#undef NSB_FC_CASE
+}
+
 // out ~= M^{-1} b by a degree-k Chebyshev-Jacobi polynomial (zero initial
 // guess) targeting the interval [lmax/ratio, lmax] of D^{-1} M.
-void cheb_solve(nsb_ctx *c, const CsrDev &M, const double *dinv, const double *b, double *out, double *scratch,
-                double *d, int k, double lmax, double ratio) {
-  const int64_t n = M.n_rows;
+void cheb_solve(nsb_ctx *c, const CsrDev *M /* nullptr: the velocity block F */, const double *dinv, const double *b,
+                double *out, double *scratch, double *d, int k, double lmax, double ratio) {
+  const int64_t n = M ? M->n_rows : (int64_t)c->n_u;
   const double lmin = lmax / ratio, theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   double *z = ((k - 1) % 2 == 0) ? out : scratch, *zn = ((k - 1) % 2 == 0) ? scratch : out;
   NSB_LAUNCH(c, cheb_first_kernel, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, z);
   double rho = 1.0 / sigma;
   for (int i = 1; i < k; ++i) {
     const double rho_new = 1.0 / (2.0 * sigma - rho);
-    cheb_sweep(c, M, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta);
+    if (M)
+      cheb_sweep(c, *M, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta);
+    else
+      fs_cheb_sweep(c, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta);
     std::swap(z, zn);
     rho = rho_new;
   }
@@ -189,13 +242,16 @@ __global__ void eig_seed_kernel(int64_t n, double *v) {
 }
 
 // lambda_max(D^-1 M) by power iteration, warm-started from `v`
-double power_lmax(nsb_ctx *c, const CsrDev &M, const double *dinv, double *v, double *w, int iters) {
-  const int64_t n = M.n_rows;
+double power_lmax(nsb_ctx *c, const CsrDev *M /* nullptr: F */, const double *dinv, double *v, double *w, int iters) {
+  const int64_t n = M ? M->n_rows : (int64_t)c->n_u;
   double *h = c->hdev.p;
   multi_dot(c, nullptr, 0, 0, v, n, true, h);
   NSB_LAUNCH(c, normalize_kernel, kRedBlocks, 256, n, h, v, v);
   for (int i = 0; i < iters; ++i) {
-    spmv(c, M, 3, v, nullptr, dinv, w);
+    if (M)
+      spmv(c, *M, 3, v, nullptr, dinv, w);
+    else
+      fs_apply(c, 3, false, v, nullptr, dinv, w);
     multi_dot(c, nullptr, 0, 0, w, n, true, h);
     NSB_LAUNCH(c, normalize_kernel, kRedBlocks, 256, n, h, w, v);
   }
@@ -252,11 +308,40 @@ void symbolic_schur(nsb_ctx *c) {
   upload_pattern(c, c->s, np, np, rp.data(), ci.data());
 }
 
+// canonical A00 = F_s (x) ones(dim,dim) pattern and values, built on demand
+void ensure_canonical_pattern(nsb_ctx *c) {
+  if (c->a00.have) return;
+  if (!c->fs.have) throw ArgError("A00 pattern not set");
+  const int d = c->dim;
+  CsrDev &A = c->a00;
+  A.n_rows = A.n_cols = c->n_u;
+  A.nnz = c->fs.nnz * d * d;
+  A.rowptr.alloc((size_t)c->n_u + 1, &c->dev_bytes);
+  A.colind.alloc((size_t)A.nnz, &c->dev_bytes);
+  if (d == 2)
+    NSB_LAUNCH(c, expand_node_pattern_kernel<2>, blocks_for(c->fs.n_rows * 32), 256, c->fs.n_rows, c->fs.rowptr.p,
+               c->fs.colind.p, A.rowptr.p, A.colind.p);
+  else
+    NSB_LAUNCH(c, expand_node_pattern_kernel<3>, blocks_for(c->fs.n_rows * 32), 256, c->fs.n_rows, c->fs.rowptr.p,
+               c->fs.colind.p, A.rowptr.p, A.colind.p);
+  A.have = true;
+}
+void materialize_canonical_values(nsb_ctx *c) {
+  ensure_canonical_pattern(c);
+  if (!c->a00.val.p) c->a00.val.alloc((size_t)c->a00.nnz, &c->dev_bytes);
+  if (c->dim == 2)
+    NSB_LAUNCH(c, expand_values_kernel<2>, blocks_for(c->fs.n_rows * 32), 256, c->fs.n_rows, c->fs.rowptr.p,
+               c->fs.val.p, c->a00.val.p);
+  else
+    NSB_LAUNCH(c, expand_values_kernel<3>, blocks_for(c->fs.n_rows * 32), 256, c->fs.n_rows, c->fs.rowptr.p,
+               c->fs.val.p, c->a00.val.p);
+}
+
 void finalize_setup(nsb_ctx *c) {
   if (c->finalized) return;
-  if (!c->have_mesh || !c->have_dofs || !c->a00.have || !c->a01.have || !c->a10.have)
+  if (!c->have_mesh || !c->have_dofs || !c->fs.have || !c->a01.have || !c->a10.have)
     throw ArgError("setup incomplete: need nsb_set_mesh, nsb_set_dofs and the A00/A01/A10 patterns");
-  if (c->a00.n_rows != c->n_u || c->a01.n_rows != c->n_u || c->a10.n_rows != c->n_p)
+  if (c->fs.n_rows * c->dim != c->n_u || c->a01.n_rows != c->n_u || c->a10.n_rows != c->n_p)
     throw ArgError("pattern sizes do not match n_u/n_p");
   if (!c->have_quad) {
     if (!fill_fe_tables(c->dim, c->quad_rule, c->fe_host)) throw ArgError("bad quadrature rule");
@@ -275,15 +360,15 @@ void finalize_setup(nsb_ctx *c) {
   const int64_t per = NN * NN + 2 * NN * NV;
   if (c->dim == 2)
     NSB_LAUNCH(c, build_slots_kernel<2>, blocks_for(c->n_cells * per), 256, c->n_cells, c->cell_nodes.p,
-               c->cell_pverts.p, c->a00.view(), c->a01.view(), c->a10.view(), c->slot00.p, c->slot01.p, c->slot10.p,
+               c->cell_pverts.p, c->fs.view(), c->a01.view(), c->a10.view(), c->slot00.p, c->slot01.p, c->slot10.p,
                c->errflag.p);
   else
     NSB_LAUNCH(c, build_slots_kernel<3>, blocks_for(c->n_cells * per), 256, c->n_cells, c->cell_nodes.p,
-               c->cell_pverts.p, c->a00.view(), c->a01.view(), c->a10.view(), c->slot00.p, c->slot01.p, c->slot10.p,
+               c->cell_pverts.p, c->fs.view(), c->a01.view(), c->a10.view(), c->slot00.p, c->slot01.p, c->slot10.p,
                c->errflag.p);
-  c->diag00.alloc(c->n_u, &c->dev_bytes);
+  c->diagF.alloc((size_t)c->fs.n_rows, &c->dev_bytes);
   c->diagS.alloc(c->n_p, &c->dev_bytes);
-  NSB_LAUNCH(c, diag_positions_kernel, blocks_for(c->n_u), 256, c->a00.view(), c->diag00.p, c->errflag.p);
+  NSB_LAUNCH(c, diag_positions_kernel, blocks_for(c->fs.n_rows), 256, c->fs.view(), c->diagF.p, c->errflag.p);
   NSB_LAUNCH(c, diag_positions_kernel, blocks_for(c->n_p), 256, c->s.view(), c->diagS.p, c->errflag.p);
   check_errflag(c, "nsb_finalize_setup");
   const int64_t N = c->N;
@@ -342,10 +427,10 @@ void assemble_launch(nsb_ctx *c) {
   A.slot00 = c->slot00.p;
   A.slot01 = c->slot01.p;
   A.slot10 = c->slot10.p;
-  A.rowptr00 = c->a00.rowptr.p;
+  A.nptr = c->fs.rowptr.p;
   A.rowptr01 = c->a01.rowptr.p;
   A.rowptr10 = c->a10.rowptr.p;
-  A.val00 = c->a00.val.p;
+  A.fs_val = c->fs.val.p;
   A.val01 = c->a01.val.p;
   A.val10 = c->a10.val.p;
   A.rhs = c->rhs.p;
@@ -354,7 +439,7 @@ void assemble_launch(nsb_ctx *c) {
   A.inv_dt = 1.0 / c->dt;
   A.nu = c->nu;
   // reference :154-156
-  c->a00.val.zero(c->stream);
+  c->fs.val.zero(c->stream);
   c->a01.val.zero(c->stream);
   c->a10.val.zero(c->stream);
   c->rhs.zero(c->stream);
@@ -367,26 +452,49 @@ void assemble_launch(nsb_ctx *c) {
   else
     NSB_LAUNCH(c, (assemble_cells_kernel<3, 14>), grid, kAsmWarps * 32, A);
   // reference :326-328
-  if (c->bc_dofs.n) {
-    NSB_LAUNCH(c, first_diag_kernel, 1, 32, c->a00.val.p, c->diag00.p, (int64_t)c->n_u, c->first_diag.p);
-    NSB_LAUNCH(c, apply_dirichlet_kernel, blocks_for((int64_t)c->bc_dofs.n * 32), 256, (int64_t)c->bc_dofs.n,
-               c->bc_dofs.p, c->bc_vals.p, c->bc_factor, c->a00.view(), c->a01.view(), c->diag00.p, c->first_diag.p,
-               c->bc_mode, c->rhs.p, c->sol.p);
+  if (c->bc_nodes.n) {
+    const int64_t nb = (int64_t)c->bc_nodes.n;
+    NSB_LAUNCH(c, first_diag_kernel, 1, 32, c->fs.val.p, c->diagF.p, c->fs.n_rows, c->first_diag.p);
+    if (c->dim == 2)
+      NSB_LAUNCH(c, apply_dirichlet_kernel<2>, blocks_for(nb * 32), 256, nb, c->bc_nodes.p, c->bc_vals.p, c->bc_factor,
+                 c->fs.view(), c->a01.view(), c->diagF.p, c->first_diag.p, c->bc_mode, c->rhs.p, c->sol.p);
+    else
+      NSB_LAUNCH(c, apply_dirichlet_kernel<3>, blocks_for(nb * 32), 256, nb, c->bc_nodes.p, c->bc_vals.p, c->bc_factor,
+                 c->fs.view(), c->a01.view(), c->diagF.p, c->first_diag.p, c->bc_mode, c->rhs.p, c->sol.p);
   }
 }
 
 // ---- preconditioner -------------------------------------------------------
+// Default inner-sweep parameters.  F = M/dt + nu K + C is mass dominated for
+// the benchmark time steps: a degree-3 polynomial on [lmax/6, lmax] reaches the
+// reference's 1e-2 inner tolerance.  S = B D^-1 Bt behaves like a Laplacian on
+// the pressure mesh, cond(D_S^-1 S) ~ (L/h)^2 ~ n_p^(2/dim): the interval
+// ratio follows that estimate and the degree is 1.5 sqrt(ratio).
+void auto_inner(nsb_ctx *c) {
+  if (c->sweepsF <= 0) {
+    c->sweepsF = 3;
+    c->ratioF = 6.0;
+  }
+  if (c->sweepsS <= 0) {
+    const double np = (double)c->n_p;
+    c->ratioS = std::max(30.0, (c->dim == 3 ? 1.7 : 0.35) * std::pow(np, 2.0 / c->dim));
+    c->sweepsS = std::max(4, (int)std::lround(1.5 * std::sqrt(c->ratioS)));
+  }
+}
+
 // PreconditionASIMPLE::initialize, reference :934-963
 void prec_init(nsb_ctx *c) {
-  NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_u), 256, (int64_t)c->n_u, c->a00.val.p, c->diag00.p, c->di.p);
+  auto_inner(c);
+  NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_u), 256, (int64_t)c->n_u, c->dim, c->fs.val.p, c->diagF.p,
+             c->di.p);
   if (c->prec != NSB_PREC_ASIMPLE) return;
   c->s.val.zero(c->stream);
   NSB_LAUNCH(c, schur_numeric_kernel, blocks_for((int64_t)c->n_p * 32), 256, c->a10.view(), c->a01.view(), c->di.p,
              c->s.view());
-  NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_p), 256, (int64_t)c->n_p, c->s.val.p, c->diagS.p, c->dis.p);
+  NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_p), 256, (int64_t)c->n_p, 1, c->s.val.p, c->diagS.p, c->dis.p);
   const int its = c->eig_warm ? 6 : 30;
-  c->lamF = 1.05 * power_lmax(c, c->a00, c->di.p, c->eig_u.p, c->eig_w.p, its);
-  c->lamS = 1.05 * power_lmax(c, c->s, c->dis.p, c->eig_p.p, c->eig_w.p, its);
+  c->lamF = 1.05 * power_lmax(c, nullptr, c->di.p, c->eig_u.p, c->eig_w.p, its);
+  c->lamS = 1.05 * power_lmax(c, &c->s, c->dis.p, c->eig_p.p, c->eig_w.p, its);
   c->eig_warm = true;
 }
 
@@ -400,11 +508,11 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
     return;
   }
   // vec0 ~= F^-1 src0                                   (:978-981)
-  cheb_solve(c, c->a00, c->di.p, src, c->vec0.p, c->chz_u.p, c->chd_u.p, c->sweepsF, c->lamF, c->ratioF);
+  cheb_solve(c, nullptr, c->di.p, src, c->vec0.p, c->chz_u.p, c->chd_u.p, c->sweepsF, c->lamF, c->ratioF);
   // vec1 = src1 - B vec0                                 (:982-983)
   spmv(c, c->a10, 1, c->vec0.p, src + nu, nullptr, c->vec1.p);
   // dst1 ~= S^-1 vec1, then dst1 *= -1/alpha             (:986-990)
-  cheb_solve(c, c->s, c->dis.p, c->vec1.p, c->chz_p2.p, c->chz_p.p, c->chd_p.p, c->sweepsS, c->lamS, c->ratioS);
+  cheb_solve(c, &c->s, c->dis.p, c->vec1.p, c->chz_p2.p, c->chz_p.p, c->chd_p.p, c->sweepsS, c->lamS, c->ratioS);
   NSB_LAUNCH(c, scale_kernel, blocks_for(np), 256, np, -1.0 / c->alpha, c->chz_p2.p, dst + nu);
   // dst0 = vec0 - Di .* (Bt dst1)                        (:992-994)
   spmv(c, c->a01, 2, dst + nu, c->vec0.p, c->di.p, dst);
@@ -588,9 +696,33 @@ int nsb_set_pattern(nsb_ctx *c, int block, int64_t n_rows, const int64_t *rowptr
     const int64_t nu = c->n_u, np = c->n_p;
     switch (block) {
       case NSB_A00:
+      {
         if (n_rows != nu) throw ArgError("A00 must have n_u rows");
-        upload_pattern(c, c->a00, nu, nu, rowptr, colind);
+        const int d = c->dim;
+        const int64_t nn = nu / d, nnz = rowptr[n_rows];
+        if (nnz % (d * d) != 0) throw StructError("A00 pattern is not nodes (x) ones(dim,dim)");
+        DevBuf<int64_t> rp;
+        DevBuf<uint32_t> ci;
+        rp.upload(rowptr, (size_t)n_rows + 1, c->stream);
+        ci.upload(colind, (size_t)nnz, c->stream);
+        CsrDev &F = c->fs;
+        F.n_rows = F.n_cols = nn;
+        F.nnz = nnz / (d * d);
+        F.rowptr.alloc((size_t)nn + 1, &c->dev_bytes);
+        F.colind.alloc((size_t)F.nnz, &c->dev_bytes);
+        F.val.alloc((size_t)F.nnz, &c->dev_bytes);
+        F.val.zero(c->stream);
+        if (d == 2)
+          NSB_LAUNCH(c, compress_pattern_kernel<2>, blocks_for(nn * 32), 256, nn, rp.p, ci.p, F.rowptr.p, F.colind.p,
+                     c->errflag.p);
+        else
+          NSB_LAUNCH(c, compress_pattern_kernel<3>, blocks_for(nn * 32), 256, nn, rp.p, ci.p, F.rowptr.p, F.colind.p,
+                     c->errflag.p);
+        check_errflag(c, "nsb_set_pattern(A00)");
+        F.have = true;
+        c->a00.have = false;
         break;
+      }
       case NSB_A01:
         if (n_rows != nu) throw ArgError("A01 must have n_u rows");
         upload_pattern(c, c->a01, nu, np, rowptr, colind);
@@ -618,26 +750,8 @@ int nsb_set_node_pattern(nsb_ctx *c, int64_t n_nodes, const int64_t *rowptr, con
   return guarded(c, [&] {
     if (!c->have_dofs) throw ArgError("nsb_set_node_pattern: call nsb_set_dofs first");
     if (n_nodes * c->dim != (int64_t)c->n_u) throw ArgError("nsb_set_node_pattern: n_nodes*dim != n_u");
-    const int d = c->dim;
-    DevBuf<int64_t> nptr;
-    DevBuf<uint32_t> ncol;
-    nptr.upload(rowptr, (size_t)n_nodes + 1, c->stream);
-    ncol.upload(colind, (size_t)rowptr[n_nodes], c->stream);
-    CsrDev &A = c->a00;
-    A.n_rows = A.n_cols = c->n_u;
-    A.nnz = rowptr[n_nodes] * d * d;
-    A.rowptr.alloc((size_t)c->n_u + 1, &c->dev_bytes);
-    A.colind.alloc((size_t)A.nnz, &c->dev_bytes);
-    A.val.alloc((size_t)A.nnz, &c->dev_bytes);
-    A.val.zero(c->stream);
-    if (d == 2)
-      NSB_LAUNCH(c, expand_node_pattern_kernel<2>, blocks_for(n_nodes * 32), 256, n_nodes, nptr.p, ncol.p,
-                 A.rowptr.p, A.colind.p);
-    else
-      NSB_LAUNCH(c, expand_node_pattern_kernel<3>, blocks_for(n_nodes * 32), 256, n_nodes, nptr.p, ncol.p,
-                 A.rowptr.p, A.colind.p);
-    NSB_CUDA(cudaStreamSynchronize(c->stream));
-    A.have = true;
+    upload_pattern(c, c->fs, n_nodes, n_nodes, rowptr, colind);
+    c->a00.have = false;
     c->finalized = false;
   });
 }
@@ -683,8 +797,8 @@ int nsb_set_solver(nsb_ctx *c, double gmres_rtol, int restart, int max_it, doubl
 }
 int nsb_set_inner(nsb_ctx *c, int sweeps_F, double eig_ratio_F, int sweeps_S, double eig_ratio_S) {
   return guarded(c, [&] {
-    if (sweeps_F < 1 || sweeps_S < 1 || !(eig_ratio_F > 1) || !(eig_ratio_S > 1))
-      throw ArgError("nsb_set_inner: sweeps >= 1 and eig ratios > 1 required");
+    if ((sweeps_F > 0 && !(eig_ratio_F > 1)) || (sweeps_S > 0 && !(eig_ratio_S > 1)))
+      throw ArgError("nsb_set_inner: eig ratios must exceed 1 (sweeps <= 0 selects the automatic choice)");
     c->sweepsF = sweeps_F;
     c->ratioF = eig_ratio_F;
     c->sweepsS = sweeps_S;
@@ -708,8 +822,29 @@ int nsb_get_solution(nsb_ctx *c, double *x) {
 int nsb_set_dirichlet(nsb_ctx *c, int64_t n_bc, const uint32_t *dofs, const double *values) {
   return guarded(c, [&] {
     if (n_bc < 0 || (n_bc > 0 && (!dofs || !values))) throw ArgError("nsb_set_dirichlet: null input");
-    c->bc_dofs.upload(dofs, (size_t)n_bc, c->stream, &c->dev_bytes);
-    c->bc_vals.upload(values, (size_t)n_bc, c->stream, &c->dev_bytes);
+    const int d = c->dim;
+    // the velocity block is stored as F_s (x) I_dim: a constrained node must be
+    // constrained in all its components (true for the reference, :300-324)
+    std::vector<int64_t> order((size_t)n_bc);
+    for (int64_t i = 0; i < n_bc; ++i) order[i] = i;
+    if (!std::is_sorted(dofs, dofs + n_bc))
+      std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return dofs[a] < dofs[b]; });
+    if (n_bc % d != 0) throw StructError("nsb_set_dirichlet: component-wise constraints are not supported");
+    std::vector<uint32_t> nodes((size_t)(n_bc / d));
+    std::vector<double> vals((size_t)n_bc);
+    for (int64_t j = 0; j < n_bc / d; ++j) {
+      const uint32_t u0 = dofs[order[j * d]];
+      if (u0 % d != 0 || (c->n_u && u0 + d > c->n_u))
+        throw StructError("nsb_set_dirichlet: constrained dofs must come as whole velocity nodes");
+      for (int k = 0; k < d; ++k) {
+        if (dofs[order[j * d + k]] != u0 + k)
+          throw StructError("nsb_set_dirichlet: constrained dofs must come as whole velocity nodes");
+        vals[j * d + k] = values[order[j * d + k]];
+      }
+      nodes[j] = u0 / d;
+    }
+    c->bc_nodes.upload(nodes.data(), nodes.size(), c->stream, &c->dev_bytes);
+    c->bc_vals.upload(vals.data(), vals.size(), c->stream, &c->dev_bytes);
     c->bc_factor = 1.0;
     NSB_CUDA(cudaStreamSynchronize(c->stream));
   });
@@ -806,6 +941,7 @@ static CsrDev *block_of(nsb_ctx *c, int block) {
 
 int nsb_get_matrix_values(nsb_ctx *c, int block, double *vals) {
   return guarded(c, [&] {
+    if (block == NSB_A00) materialize_canonical_values(c);
     CsrDev *A = block_of(c, block);
     if (!A || !A->have) throw ArgError("nsb_get_matrix_values: block not set");
     A->val.download(vals, c->stream);
@@ -813,6 +949,7 @@ int nsb_get_matrix_values(nsb_ctx *c, int block, double *vals) {
 }
 int nsb_get_pattern(nsb_ctx *c, int block, int64_t *rowptr, uint32_t *colind) {
   return guarded(c, [&] {
+    if (block == NSB_A00) ensure_canonical_pattern(c);
     CsrDev *A = block_of(c, block);
     if (!A || !A->have) throw ArgError("nsb_get_pattern: block not set");
     A->rowptr.download(rowptr, c->stream);
@@ -820,6 +957,7 @@ int nsb_get_pattern(nsb_ctx *c, int block, int64_t *rowptr, uint32_t *colind) {
   });
 }
 int64_t nsb_nnz(const nsb_ctx *c, int block) {
+  if (block == NSB_A00) return c->fs.have ? c->fs.nnz * c->dim * c->dim : -1;
   const CsrDev *A = block_of(const_cast<nsb_ctx *>(c), block);
   return A && A->have ? A->nnz : -1;
 }
@@ -845,13 +983,18 @@ int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
     ensure_krylov(c);
     const bool flush = (which & 0x100) != 0;
     which &= 0xff;
+    if (which == 0) {
+      materialize_canonical_values(c);
+      NSB_CUDA(cudaStreamSynchronize(c->stream));
+    }
     if (flush && !c->flush.p) c->flush.alloc((size_t)256 << 20, &c->dev_bytes);
     double total = 0;
     for (int r = 0; r < reps; ++r) {
       if (flush) NSB_CUDA(cudaMemsetAsync(c->flush.p, r & 0xff, c->flush.n, c->stream));
       NSB_CUDA(cudaEventRecord(c->ev0, c->stream));
       switch (which) {
-        case 0: block_spmv(c, c->sol.p, c->tmpN.p); break;
+        case 0: block_spmv_canonical(c, c->sol.p, c->tmpN.p); break;
+        case 5: block_spmv(c, c->sol.p, c->tmpN.p); break;
         case 1: assemble_launch(c); break;
         case 2: prec_apply(c, c->rhs.p, c->V.p); break;
         case 3:
@@ -859,7 +1002,8 @@ int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
           NSB_LAUNCH(c, schur_numeric_kernel, blocks_for((int64_t)c->n_p * 32), 256, c->a10.view(), c->a01.view(),
                      c->di.p, c->s.view());
           break;
-        case 4: cheb_sweep(c, c->a00, c->di.p, c->rhs.p, c->vec0.p, c->chd_u.p, c->chz_u.p, 0.5, 0.5); break;
+        case 4: fs_cheb_sweep(c, c->di.p, c->rhs.p, c->vec0.p, c->chd_u.p, c->chz_u.p, 0.5, 0.5); break;
+        case 6: cheb_sweep(c, c->s, c->dis.p, c->vec1.p, c->chz_p.p, c->chd_p.p, c->chz_p2.p, 0.5, 0.5); break;
         default: throw ArgError("nsb_bench_kernel: unknown kernel id");
       }
       NSB_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -883,7 +1027,7 @@ int nsb_info(const nsb_ctx *c, int64_t out[9]) {
   out[0] = c->n_u;
   out[1] = c->n_p;
   out[2] = c->n_cells;
-  out[3] = c->a00.nnz;
+  out[3] = c->fs.nnz * c->dim * c->dim;
   out[4] = c->a01.nnz;
   out[5] = c->a10.nnz;
   out[6] = c->s.nnz;

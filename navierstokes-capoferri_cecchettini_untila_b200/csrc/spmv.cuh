@@ -95,6 +95,97 @@ __global__ void __launch_bounds__(256) cheb_sweep_kernel(CsrView M, const double
   }
 }
 
+// ---------------------------------------------------------------------------
+// Node-block form of the velocity block: A00 = F_s (x) I_dim, stored as the
+// scalar node-level CSR F_s acting on vectors interleaved as [node][dim]
+// (exactly the canonical dof order dim*node + c).  Per stored non-zero 12 B
+// are streamed for 2*dim flops instead of 12*dim^2 B in the canonical block.
+// ---------------------------------------------------------------------------
+template <int DIM, int L>
+__device__ __forceinline__ void node_row_dot(const CsrView &F, int64_t node, const double *__restrict__ x, int sub,
+                                             double (&s)[DIM]) {
+  const int64_t b = __ldg(F.rowptr + node), e = __ldg(F.rowptr + node + 1);
+  double t[DIM];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) t[c] = 0.0;
+  int64_t k = b + sub;
+  for (; k + L < e; k += 2 * L) {
+    const double v0 = ld_stream(F.val + k), v1 = ld_stream(F.val + k + L);
+    const double *x0 = x + (size_t)DIM * ld_stream(F.colind + k), *x1 = x + (size_t)DIM * ld_stream(F.colind + k + L);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+      s[c] += v0 * __ldg(x0 + c);
+      t[c] += v1 * __ldg(x1 + c);
+    }
+  }
+  if (k < e) {
+    const double v0 = ld_stream(F.val + k);
+    const double *x0 = x + (size_t)DIM * ld_stream(F.colind + k);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) s[c] += v0 * __ldg(x0 + c);
+  }
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) s[c] += t[c];
+}
+
+// velocity rows of the block product:  y_u = F x_u (+ A01 x_p when a01.rowptr)
+//   MODE 0: y = ..., MODE 3: y = d .* (F x)   (power iteration on D^-1 F)
+template <int DIM, int L, int MODE>
+__global__ void __launch_bounds__(256) fs_apply_kernel(CsrView F, CsrView a01, const double *__restrict__ xu,
+                                                       const double *__restrict__ xp, const double *__restrict__ d,
+                                                       double *__restrict__ y) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int sub = threadIdx.x % L;
+  const bool live = g < F.n_rows;
+  double s[DIM];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) s[c] = 0.0;
+  if (live) {
+    node_row_dot<DIM, L>(F, g, xu, sub, s);
+    if (a01.rowptr != nullptr) {
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) s[c] += row_dot<L>(a01, (int64_t)DIM * g + c, xp, sub);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) s[c] = sub_reduce<L>(s[c]);
+  if (sub == 0 && live) {
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+      const int64_t i = (int64_t)DIM * g + c;
+      y[i] = MODE == 3 ? d[i] * s[c] : s[c];
+    }
+  }
+}
+
+// Chebyshev-Jacobi sweep on F (see cheb_sweep_kernel), node-block form
+template <int DIM, int L>
+__global__ void __launch_bounds__(256) fs_cheb_sweep_kernel(CsrView F, const double *__restrict__ dinv,
+                                                            const double *__restrict__ b,
+                                                            const double *__restrict__ z, double *__restrict__ d,
+                                                            double *__restrict__ znew, double c1, double c2) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int sub = threadIdx.x % L;
+  const bool live = g < F.n_rows;
+  double s[DIM];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) s[c] = 0.0;
+  if (live) node_row_dot<DIM, L>(F, g, z, sub, s);
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) s[c] = sub_reduce<L>(s[c]);
+  if (live && sub < DIM) {
+    // lane c of the sub-warp finishes component c
+    double sc = s[0];
+#pragma unroll
+    for (int c = 1; c < DIM; ++c)
+      if (sub == c) sc = s[c];
+    const int64_t i = (int64_t)DIM * g + sub;
+    const double dn = c1 * d[i] + c2 * dinv[i] * (b[i] - sc);
+    d[i] = dn;
+    znew[i] = z[i] + dn;
+  }
+}
+
 // first sweep with zero initial guess: d = z = Dinv .* b / theta
 __global__ void cheb_first_kernel(int64_t n, const double *__restrict__ dinv, const double *__restrict__ b,
                                   double inv_theta, double *__restrict__ d, double *__restrict__ z) {
@@ -106,10 +197,11 @@ __global__ void cheb_first_kernel(int64_t n, const double *__restrict__ dinv, co
   }
 }
 
-__global__ void diag_inverse_kernel(int64_t n, const double *__restrict__ val, const int64_t *__restrict__ diagpos,
-                                    double *__restrict__ dinv) {
+// dinv[i] = 1 / M[i / rep, i / rep]  (rep = dim for the node-block F, 1 for S)
+__global__ void diag_inverse_kernel(int64_t n, int rep, const double *__restrict__ val,
+                                    const int64_t *__restrict__ diagpos, double *__restrict__ dinv) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dinv[i] = 1.0 / val[diagpos[i]];
+  if (i < n) dinv[i] = 1.0 / val[diagpos[i / rep]];
 }
 
 // S = B diag(Di) Bt on the precomputed pattern of S (reference :956).  One warp
