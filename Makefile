@@ -10,7 +10,7 @@ CXXFLAGS := -O3 -march=x86-64-v3 -std=c++17 -fPIC -fopenmp -Wall -Wextra -Wno-un
 NVFLAGS  := -ccbin /usr/bin/g++ -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
             -Xcompiler -fPIC,-fopenmp,-Wall -Xptxas -v
 
-HOST_SRC := $(PKG)/host/mesh.cpp $(PKG)/host/fespace.cpp $(PKG)/host/nsb_host_capi.cpp
+HOST_SRC := $(PKG)/host/mesh.cpp $(PKG)/host/fespace.cpp $(PKG)/host/distribute.cpp $(PKG)/host/nsb_host_capi.cpp
 HOST_HDR := $(wildcard $(PKG)/host/*.hpp) include/nsb_host.h
 CU_SRC   := $(PKG)/csrc/nsb_capi.cu
 CU_HDR   := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/nsb.h

@@ -62,6 +62,26 @@ int nsh_array(const nsh_problem *, const char *name, const void **data, int64_t 
  * GridTools::partition_triangulation -> METIS, reference :19). */
 int nsh_partition(nsh_problem *, int n_parts);
 
+/* ---- domain decomposition over the GPUs of one box --------
+ * Local view of rank `rank` out of n_parts after nsh_partition(n_parts):
+ * owned + ghost velocity nodes in local numbering, replicated pressure in the
+ * partition-contiguous ("distributed") numbering, local CSR patterns, halo
+ * send/receive lists, owned Dirichlet nodes and obstacle faces.  Stands in for
+ * parallel::fullydistributed::Triangulation + the Epetra maps the reference
+ * builds at NavierStokes.cpp:19-23, 71-86, 113-127. */
+typedef struct nsh_local nsh_local;
+int nsh_localize(const nsh_problem *, int n_parts, int rank, nsh_local **out);
+void nsh_local_free(nsh_local *);
+/* sizes: [0] n_own [1] n_ghost [2] n_p [3] n_p_own [4] p_offset [5] n_local_cells
+ * [6] n_neighbors [7] n_bc_nodes [8] n_force_faces [9] n_nodes_global [10] node_offset */
+int nsh_local_sizes(const nsh_local *, int64_t out[11]);
+/* "node_offset" "p_offset" "node_perm" "p_perm" "ghost_dist" "cells"
+ * "cell_verts" "cell_nodes" "cell_pverts" (u32); "<blk>.rowptr" (i64) /
+ * "<blk>.colind" (u32) for blk in fs,a01,a10,s; "neighbors" (i32) "send_ptr"
+ * "recv_ptr" (i64) "send_idx" (u32); "bc_nodes" (u32) "bc_values" (f64);
+ * "ff.cell" (u32) "ff.normal" "ff.measure" (f64). */
+int nsh_local_array(const nsh_local *, const char *name, const void **data, int64_t *count, int *elem_bytes);
+
 #ifdef __cplusplus
 }
 #endif

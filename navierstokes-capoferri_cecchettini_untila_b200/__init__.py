@@ -67,6 +67,10 @@ def host_lib():
         L.nsh_sizes.argtypes = [C.c_void_p, _c_i64p]
         L.nsh_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), _c_i64p, C.POINTER(C.c_int)]
         L.nsh_partition.argtypes = [C.c_void_p, C.c_int]
+        L.nsh_localize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.nsh_local_free.argtypes = [C.c_void_p]
+        L.nsh_local_sizes.argtypes = [C.c_void_p, _c_i64p]
+        L.nsh_local_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), _c_i64p, C.POINTER(C.c_int)]
         _host = L
     return _host
 
@@ -161,6 +165,54 @@ class Problem:
         try:
             if self._h:
                 self._L.nsh_problem_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class LocalProblem:
+    """Rank-local view of a partitioned :class:`Problem` (``nsh_local``)."""
+    _F64 = {"bc_values", "ff.normal", "ff.measure"}
+    _I32 = {"neighbors"}
+    _I64 = {"send_ptr", "recv_ptr"}
+
+    def __init__(self, prob: Problem, n_parts: int, rank: int):
+        self._L = host_lib()
+        self._prob = prob  # keep the parent alive
+        out = C.c_void_p()
+        Problem._chk(self._L.nsh_localize(prob._h, n_parts, rank, C.byref(out)))
+        self._h = out
+        self.rank, self.n_parts = rank, n_parts
+
+    def sizes(self):
+        out = (C.c_int64 * 11)()
+        Problem._chk(self._L.nsh_local_sizes(self._h, out))
+        keys = ["n_own", "n_ghost", "n_p", "n_p_own", "p_offset", "n_local_cells", "n_neighbors", "n_bc_nodes",
+                "n_force_faces", "n_nodes_global", "node_offset"]
+        return dict(zip(keys, [int(x) for x in out]))
+
+    def array(self, name) -> np.ndarray:
+        data, count, eb = C.c_void_p(), C.c_int64(), C.c_int()
+        Problem._chk(self._L.nsh_local_array(self._h, name.encode(), C.byref(data), C.byref(count), C.byref(eb)))
+        if name in self._F64:
+            dt = np.float64
+        elif name in self._I32:
+            dt = np.int32
+        elif name in self._I64 or name.endswith("rowptr"):
+            dt = np.int64
+        else:
+            dt = np.uint32
+        if count.value == 0:
+            return np.zeros(0, dt)
+        buf = (C.c_char * (count.value * eb.value)).from_address(data.value)
+        a = np.frombuffer(buf, dtype=dt)
+        a.flags.writeable = False
+        return a
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.nsh_local_free(self._h)
                 self._h = None
         except Exception:
             pass

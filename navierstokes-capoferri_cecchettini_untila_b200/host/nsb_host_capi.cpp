@@ -7,10 +7,14 @@
 #include <stdexcept>
 #include <string>
 
+#include "distribute.hpp"
 #include "problem.hpp"
 
 struct nsh_problem {
   nsb::Problem p;
+};
+struct nsh_local {
+  nsb::LocalProblem l;
 };
 
 namespace {
@@ -203,6 +207,72 @@ int nsh_partition(nsh_problem *P, int n_parts) {
     if (n_parts < 1) throw std::runtime_error("nsh_partition: n_parts < 1");
     P->p.partition(n_parts);
   });
+}
+
+int nsh_localize(const nsh_problem *P, int n_parts, int rank, nsh_local **out) {
+  return guarded([&] {
+    auto *L = new nsh_local;
+    try {
+      L->l = nsb::localize(P->p, n_parts, rank);
+    } catch (...) {
+      delete L;
+      throw;
+    }
+    *out = L;
+  });
+}
+void nsh_local_free(nsh_local *L) { delete L; }
+int nsh_local_sizes(const nsh_local *L, int64_t out[11]) {
+  const nsb::LocalProblem &l = L->l;
+  out[0] = l.n_own;
+  out[1] = l.n_ghost;
+  out[2] = l.n_p;
+  out[3] = l.n_p_own();
+  out[4] = l.p_offset[l.rank];
+  out[5] = (int64_t)l.cells.size();
+  out[6] = (int64_t)l.neighbors.size();
+  out[7] = (int64_t)l.bc_nodes.size();
+  out[8] = (int64_t)l.ff_cell.size();
+  out[9] = l.n_nodes_global;
+  out[10] = l.node_offset[l.rank];
+  return 0;
+}
+int nsh_local_array(const nsh_local *L, const char *name, const void **data, int64_t *count, int *elem_bytes) {
+  const nsb::LocalProblem &l = L->l;
+  const std::string n(name);
+  auto set = [&](const auto &v) {
+    *data = v.data();
+    *count = (int64_t)v.size();
+    *elem_bytes = (int)sizeof(v[0]);
+    return 0;
+  };
+  if (n == "node_offset") return set(l.node_offset);
+  if (n == "p_offset") return set(l.p_offset);
+  if (n == "node_perm") return set(l.node_perm);
+  if (n == "p_perm") return set(l.p_perm);
+  if (n == "ghost_dist") return set(l.ghost_dist);
+  if (n == "cells") return set(l.cells);
+  if (n == "cell_verts") return set(l.cell_verts);
+  if (n == "cell_nodes") return set(l.cell_nodes);
+  if (n == "cell_pverts") return set(l.cell_pverts);
+  if (n == "neighbors") return set(l.neighbors);
+  if (n == "send_ptr") return set(l.send_ptr);
+  if (n == "recv_ptr") return set(l.recv_ptr);
+  if (n == "send_idx") return set(l.send_idx);
+  if (n == "bc_nodes") return set(l.bc_nodes);
+  if (n == "bc_values") return set(l.bc_values);
+  if (n == "ff.cell") return set(l.ff_cell);
+  if (n == "ff.normal") return set(l.ff_normal);
+  if (n == "ff.measure") return set(l.ff_measure);
+  const size_t dot = n.find('.');
+  if (dot != std::string::npos) {
+    const std::string b = n.substr(0, dot), f = n.substr(dot + 1);
+    const nsb::Csr *A = b == "fs" ? &l.fs : b == "a01" ? &l.a01 : b == "a10" ? &l.a10 : b == "s" ? &l.s : nullptr;
+    if (A && f == "rowptr") return set(A->rowptr);
+    if (A && f == "colind") return set(A->colind);
+  }
+  g_err = "nsh_local_array: unknown array '" + n + "'";
+  return -1;
 }
 
 }  // extern "C"
