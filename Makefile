@@ -31,15 +31,19 @@ $(PKG)/libnsb.so: $(CU_SRC) $(CU_HDR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRC) -cudart static -ldl 2> $(PKG)/csrc/ptxas.log || (cat $(PKG)/csrc/ptxas.log; false)
 
 DRV      := $(PKG)/drivers
+# -DNS_INPUT= is passed to BOTH translation units of a driver.  The reference defines NS_INPUT only
+# in the driver source, so its NavierStokes.cpp sees the in-class default InletVelocity::get_mean_vel()
+# (2/3) while the driver defines another one: an ODR violation whose outcome depends on inlining
+# (DESIGN.md section 7).  Here the driver's definition is used everywhere.
 DRIVER_BIN := $(DRV)/d2_test_01 $(DRV)/d2_test_02 $(DRV)/d2_test_03 $(DRV)/d2_test_naca \
               $(DRV)/d3_test_01 $(DRV)/d3_test_02 $(DRV)/d3_test_03 $(DRV)/make_mesh
 FACADE   := $(PKG)/host/NavierStokes.cpp $(PKG)/host/NavierStokes.hpp $(DRV)/driver_common.hpp
 drivers: $(DRIVER_BIN)
 $(DRV)/d2_%: $(DRV)/d2_%.cpp $(FACADE) $(PKG)/libnsb_host.so $(PKG)/libnsb.so
-	$(CXX) $(CXXFLAGS) -fPIE -DDIM=2 -I$(PKG)/host -Iinclude -o $@ $< $(PKG)/host/NavierStokes.cpp \
+	$(CXX) $(CXXFLAGS) -fPIE -DDIM=2 -DNS_INPUT= -I$(PKG)/host -Iinclude -o $@ $< $(PKG)/host/NavierStokes.cpp \
 	    -L$(PKG) -lnsb_host -lnsb -Wl,-rpath,'$$ORIGIN/..'
 $(DRV)/d3_%: $(DRV)/d3_%.cpp $(FACADE) $(PKG)/libnsb_host.so $(PKG)/libnsb.so
-	$(CXX) $(CXXFLAGS) -fPIE -DDIM=3 -I$(PKG)/host -Iinclude -o $@ $< $(PKG)/host/NavierStokes.cpp \
+	$(CXX) $(CXXFLAGS) -fPIE -DDIM=3 -DNS_INPUT= -I$(PKG)/host -Iinclude -o $@ $< $(PKG)/host/NavierStokes.cpp \
 	    -L$(PKG) -lnsb_host -lnsb -Wl,-rpath,'$$ORIGIN/..'
 $(DRV)/make_mesh: $(DRV)/make_mesh.cpp $(PKG)/libnsb_host.so
 	$(CXX) $(CXXFLAGS) -fPIE -I$(PKG)/host -o $@ $< -L$(PKG) -lnsb_host -Wl,-rpath,'$$ORIGIN/..'

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--canonical-spmv", action="store_true",
                     help="also time y = A x on the materialised canonical (reference) CSR")
     ap.add_argument("--alpha", type=float, default=0.5)
+    ap.add_argument("--schur", type=str, default="1,0,0,0,0", help="mode,nu,theta,omega,cycles of the Schur solver")
     ap.add_argument("--sweeps", type=str, default="0,0,0,0",
                     help="kF,ratioF,kS,ratioS of the inner sweeps (0 = automatic)")
     return ap.parse_args()
@@ -220,6 +221,8 @@ def main():
     dev.set_params(DT, nu)
     dev.set_solver(1e-6, 28, 10000, a.alpha)
     dev.set_inner(int(kF), float(rF) if int(kF) > 0 else 0.0, int(kS), float(rS) if int(kS) > 0 else 0.0)
+    sm = a.schur.split(",")
+    dev.set_schur_solver(int(sm[0]), int(sm[1]), float(sm[2]), float(sm[3]), int(sm[4]))
     info = dev.info()
     N = info["n_u"] + info["n_p"]
     t_setup = time.perf_counter() - t_setup

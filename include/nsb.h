@@ -87,6 +87,15 @@ int nsb_set_solver(nsb_ctx *ctx, double gmres_rtol, int restart, int max_it, dou
  * lambda_max/lambda_min of D^-1 M targeted by the polynomial.  sweeps <= 0
  * (the default) selects an automatic choice from the problem size. */
 int nsb_set_inner(nsb_ctx *ctx, int sweeps_F, double eig_ratio_F, int sweeps_S, double eig_ratio_S);
+/* Solver for the Schur block S inside aSIMPLE.  mode 0: the single-level
+ * Chebyshev-Jacobi polynomial configured by nsb_set_inner.  mode 1 (default):
+ * one V-cycle over an aggregation hierarchy whose smoother is the same
+ * Chebyshev-Jacobi sweep (smoother_sweeps per side, default 2;
+ * strength-of-connection threshold theta, default 0.08; coarse-correction
+ * scaling omega, default 1.5; `cycles` V-cycles per application, default 1).
+ * Arguments <= 0 keep the defaults. */
+int nsb_set_schur_solver(nsb_ctx *ctx, int mode, int smoother_sweeps, double strength_theta, double omega,
+                         int cycles);
 
 /* ---- state ------------------------------------------------------------ */
 int nsb_set_solution(nsb_ctx *ctx, const double *x_host);   /* n_u+n_p, host -> device */
@@ -131,10 +140,30 @@ int nsb_info(const nsb_ctx *ctx, int64_t out[9]);
 void *nsb_alloc_pinned(int64_t bytes);
 void nsb_free_pinned(void *p);
 
-/* ---- multi-GPU (one process per GPU) ---------------------------------- */
+/* ---- multi-GPU: one process per GPU of one box ------------
+ * Domain decomposition of the reference (partition_triangulation + Epetra row
+ * maps, NavierStokes.cpp:19-23, 71-86): velocity rows are distributed with a
+ * ghost halo, pressure vectors and S are replicated.  A local vector is laid
+ * out [u owned | u ghost | p] (see nsh_localize in nsb_host.h for the arrays).
+ * Call order: nsb_create, nsb_set_mesh (local cells), nsb_set_local_dofs,
+ * nsb_set_halo, nsb_comm_init, nsb_set_node_pattern / nsb_set_pattern with the
+ * local patterns (A01: owned velocity rows, A10: owned pressure rows, S: full),
+ * then as on one GPU.  nsb_set_dirichlet takes local dof ids of owned nodes;
+ * nsb_set_solution / nsb_get_solution move the local vector.  Collectives:
+ * NCCL grouped send/recv for the halo, all-reduce for dot products, S values
+ * and the force integrals, broadcast groups to replicate pressure rows. */
 /* 128-byte NCCL unique id created on rank 0 and broadcast by the caller. */
 int nsb_comm_unique_id(char id[128]);
 int nsb_comm_init(nsb_ctx *ctx, int rank, int n_ranks, const char id[128]);
+/* p_offsets: n_ranks+1 offsets of the owned pressure ranges in the distributed
+ * numbering; cell_nodes: local node ids, cell_pverts: distributed pressure ids. */
+int nsb_set_local_dofs(nsb_ctx *ctx, int rank, int n_ranks, uint32_t n_own_nodes, uint32_t n_ghost_nodes,
+                       uint32_t n_p, const uint32_t *p_offsets, const uint32_t *cell_nodes,
+                       const uint32_t *cell_pverts);
+/* For neighbour k: send the owned local nodes send_idx[send_ptr[k]..send_ptr[k+1])
+ * and receive into the ghost slots [recv_ptr[k], recv_ptr[k+1]). */
+int nsb_set_halo(nsb_ctx *ctx, int n_neighbors, const int32_t *neighbors, const int64_t *send_ptr,
+                 const uint32_t *send_idx, const int64_t *recv_ptr);
 
 #ifdef __cplusplus
 }

@@ -209,6 +209,38 @@ class LocalProblem:
         a.flags.writeable = False
         return a
 
+    # ---- canonical (single-rank) numbering <-> this rank's local vector [u owned | u ghost | p] ----
+    def _maps(self):
+        if not hasattr(self, "_canon_nodes"):
+            s = self.sizes()
+            inv = np.empty(s["n_nodes_global"], np.int64)
+            inv[self.array("node_perm").astype(np.int64)] = np.arange(s["n_nodes_global"])
+            dist = np.concatenate([np.arange(s["node_offset"], s["node_offset"] + s["n_own"], dtype=np.int64),
+                                   self.array("ghost_dist").astype(np.int64)])
+            self._canon_nodes = inv[dist]  # canonical node of every local node
+            self._n_own = s["n_own"]
+        return self._canon_nodes
+
+    def to_local(self, x_global, dim):
+        """Local vector of a canonical global vector (velocity incl. ghosts, pressure replicated)."""
+        cn = self._maps()
+        n_u = dim * self.sizes()["n_nodes_global"]
+        u = x_global[:n_u].reshape(-1, dim)[cn].ravel()
+        p = np.empty(self.sizes()["n_p"])
+        p[self.array("p_perm").astype(np.int64)] = x_global[n_u:]
+        return np.concatenate([u, p])
+
+    def owned_to_global(self, x_local, dim, out):
+        """Writes this rank's owned velocity dofs (and the replicated pressure) of a local
+        vector into the canonical global vector ``out``."""
+        cn = self._maps()
+        n_u = dim * self.sizes()["n_nodes_global"]
+        n_loc = cn.size
+        ug = out[:n_u].reshape(-1, dim)
+        ug[cn[: self._n_own]] = x_local[: dim * n_loc].reshape(-1, dim)[: self._n_own]
+        out[n_u:] = x_local[dim * n_loc:][self.array("p_perm").astype(np.int64)]
+        return out
+
     def __del__(self):
         try:
             if self._h:

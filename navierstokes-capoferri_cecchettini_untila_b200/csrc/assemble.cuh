@@ -33,6 +33,10 @@ struct AsmArgs {
   const uint16_t *slot10;       // n_cells*NV*NN
   const int64_t *nptr, *rowptr01, *rowptr10;  // nptr: node-level row offsets of F_s
   double *fs_val, *val01, *val10;
+  double *val10t;  // A10 transposed on the pattern of A01 (not touched by the Dirichlet rows); feeds S
+  // ownership (multi-GPU): rows of local nodes >= n_own_nodes and of pressure
+  // vertices outside [p_begin, p_begin + n_p_own) belong to another rank
+  uint32_t n_own_nodes, p_begin, n_p_own;
   double *rhs;
   const double *sol;  // previous-step solution (velocity part is read)
   const FeTables *fe;
@@ -59,7 +63,8 @@ __device__ __forceinline__ int64_t find_col(const uint32_t *colind, int64_t b, i
 template <int DIM>
 __global__ void build_slots_kernel(int64_t n_cells, const uint32_t *__restrict__ cell_nodes,
                                    const uint32_t *__restrict__ cell_pverts, CsrView fs, CsrView a01, CsrView a10,
-                                   uint16_t *slot00, uint16_t *slot01, uint16_t *slot10, int *err) {
+                                   uint16_t *slot00, uint16_t *slot01, uint16_t *slot10, uint32_t p_begin,
+                                   int *err) {
   constexpr int NV = DIM + 1, NN = DIM == 2 ? 6 : 10, PER = NN * NN + 2 * NN * NV;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_cells * PER) return;
@@ -68,7 +73,9 @@ __global__ void build_slots_kernel(int64_t n_cells, const uint32_t *__restrict__
   const uint32_t *nodes = cell_nodes + cell * NN, *pv = cell_pverts + cell * NV;
   if (e < NN * NN) {
     const int a = e / NN, b = e % NN;
-    const int64_t row = nodes[a], rb = fs.rowptr[row], re = fs.rowptr[row + 1];
+    const int64_t row = nodes[a];
+    if (row >= fs.n_rows) return;  // row owned by another rank
+    const int64_t rb = fs.rowptr[row], re = fs.rowptr[row + 1];
     const int64_t pos = find_col(fs.colind, rb, re, nodes[b]);
     if (pos < 0 || pos - rb > 65535) atomicExch(err, 1);
     slot00[cell * NN * NN + e] = (uint16_t)(pos - rb);
@@ -77,7 +84,9 @@ __global__ void build_slots_kernel(int64_t n_cells, const uint32_t *__restrict__
   e -= NN * NN;
   if (e < NN * NV) {
     const int a = e / NV, k = e % NV;
-    const int64_t row = (int64_t)DIM * nodes[a], rb = a01.rowptr[row], re = a01.rowptr[row + 1];
+    const int64_t row = (int64_t)DIM * nodes[a];
+    if (row >= a01.n_rows) return;
+    const int64_t rb = a01.rowptr[row], re = a01.rowptr[row + 1];
     const int64_t pos = find_col(a01.colind, rb, re, pv[k]);
     if (pos < 0 || pos - rb > 65535) atomicExch(err, 2);
     slot01[cell * NN * NV + e] = (uint16_t)(pos - rb);
@@ -86,7 +95,9 @@ __global__ void build_slots_kernel(int64_t n_cells, const uint32_t *__restrict__
   e -= NN * NV;
   {
     const int k = e / NN, a = e % NN;
-    const int64_t row = pv[k], rb = a10.rowptr[row], re = a10.rowptr[row + 1];
+    const int64_t row = (int64_t)pv[k] - p_begin;  // local row of an owned pressure vertex
+    if (row < 0 || row >= a10.n_rows) return;
+    const int64_t rb = a10.rowptr[row], re = a10.rowptr[row + 1];
     const int64_t pos = find_col(a10.colind, rb, re, DIM * nodes[a]);
     const int64_t s = (pos - rb) / DIM;
     if (pos < 0 || (pos - rb) % DIM != 0 || s > 65535) atomicExch(err, 3);
@@ -219,13 +230,16 @@ __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs 
     if (lane < NN) {
       const uint32_t node = __ldg(A.cell_nodes + cell * NN + lane);
       s_node[warp][lane] = node;
-      s_rp00[warp][lane] = __ldg(A.nptr + node);
-      const int64_t q0 = __ldg(A.rowptr01 + (int64_t)DIM * node), q1 = __ldg(A.rowptr01 + (int64_t)DIM * node + 1);
-      s_rp01[warp][lane] = q0;
-      s_len01[warp][lane] = (int)(q1 - q0);
+      if (node < A.n_own_nodes) {  // rows of nodes this rank owns
+        s_rp00[warp][lane] = __ldg(A.nptr + node);
+        const int64_t q0 = __ldg(A.rowptr01 + (int64_t)DIM * node), q1 = __ldg(A.rowptr01 + (int64_t)DIM * node + 1);
+        s_rp01[warp][lane] = q0;
+        s_len01[warp][lane] = (int)(q1 - q0);
+      } else
+        s_rp00[warp][lane] = -1;
     } else if (lane >= 16 && lane < 16 + NV) {
-      const uint32_t pv = __ldg(A.cell_pverts + cell * NV + (lane - 16));
-      s_rp10[warp][lane - 16] = __ldg(A.rowptr10 + pv);
+      const uint32_t pv = __ldg(A.cell_pverts + cell * NV + (lane - 16)) - A.p_begin;  // wraps when below p_begin
+      s_rp10[warp][lane - 16] = pv < A.n_p_own ? __ldg(A.rowptr10 + pv) : -1;
     }
     __syncwarp();
     // previous-step velocity at the cell's nodes (reference :175)
@@ -271,7 +285,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs 
         acc += s_w[q] * (A.nu * gg + s_phi[q][a] * ug);
       }
       const double v = adet * (acc + s_mhat[a][b] * A.inv_dt);
-      atomicAdd(A.fs_val + s_rp00[warp][a] + sl00[p], v);
+      if (s_rp00[warp][a] >= 0) atomicAdd(A.fs_val + s_rp00[warp][a] + sl00[p], v);
     }
     // ---- pressure-velocity coupling -> A01 and A10 (reference :222-229) ----
     const uint16_t *sl01 = A.slot01 + cell * (NN * NV), *sl10 = A.slot10 + cell * (NV * NN);
@@ -281,8 +295,12 @@ __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs 
 #pragma unroll
       for (int d = 0; d < DIM; ++d) s += Ji[d][c] * s_dhat[a][k][d];
       const double v = -adet * s;
-      atomicAdd(A.val01 + s_rp01[warp][a] + (int64_t)c * s_len01[warp][a] + sl01[a * NV + k], v);
-      atomicAdd(A.val10 + s_rp10[warp][k] + (int64_t)DIM * sl10[k * NN + a] + c, v);
+      if (s_rp00[warp][a] >= 0) {
+        const int64_t pos = s_rp01[warp][a] + (int64_t)c * s_len01[warp][a] + sl01[a * NV + k];
+        atomicAdd(A.val01 + pos, v);
+        atomicAdd(A.val10t + pos, v);
+      }
+      if (s_rp10[warp][k] >= 0) atomicAdd(A.val10 + s_rp10[warp][k] + (int64_t)DIM * sl10[k * NN + a] + c, v);
     }
     // ---- right-hand side: (u^n, v)/dt, forcing term f == 0 (reference :241-248) ----
     for (int e = lane; e < NN * DIM; e += 32) {
@@ -290,7 +308,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs 
       double s = 0;
 #pragma unroll
       for (int n = 0; n < NN; ++n) s += s_mhat[a][n] * s_U[warp][n][c];
-      atomicAdd(A.rhs + (size_t)DIM * s_node[warp][a] + c, adet * A.inv_dt * s);
+      if (s_rp00[warp][a] >= 0) atomicAdd(A.rhs + (size_t)DIM * s_node[warp][a] + c, adet * A.inv_dt * s);
     }
     __syncwarp();
   }

@@ -39,13 +39,20 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double *smem /* NV
   __syncthreads();
 }
 
+// Active entries of a (possibly distributed) vector: element e of the active
+// range lives at e for e < n1 (owned velocity dofs) and at e + gap beyond
+// (the replicated pressure part sits behind the velocity ghosts); gap = 0 on a
+// single GPU.
+__device__ __forceinline__ int64_t active_index(int64_t e, int64_t n1, int64_t gap) { return e < n1 ? e : e + gap; }
+
 // out[i] = V_i . w for i < k (V_i = V + i*ld); out[k] = w . w when with_self.
 // partials: kMaxDots * gridDim.x doubles; counter: one unsigned, zero on entry
 // and reset to zero on exit.
 __global__ void __launch_bounds__(kRedThreads) multi_dot_kernel(const double *__restrict__ V, int64_t ld, int k,
-                                                                const double *__restrict__ w, int64_t n,
-                                                                int with_self, double *__restrict__ out,
-                                                                double *partials, unsigned *counter) {
+                                                                const double *__restrict__ w, int64_t n, int64_t n1,
+                                                                int64_t gap, int with_self,
+                                                                double *__restrict__ out, double *partials,
+                                                                unsigned *counter) {
   __shared__ double smem[kDotChunk * (kRedThreads / 32)];
   __shared__ bool is_last;
   const int total = k + (with_self ? 1 : 0);
@@ -54,7 +61,8 @@ __global__ void __launch_bounds__(kRedThreads) multi_dot_kernel(const double *__
 #pragma unroll
     for (int j = 0; j < kDotChunk; ++j) acc[j] = 0.0;
     const int cnt = min(kDotChunk, total - c0);
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t e = active_index(a, n1, gap);
       const double we = w[e];
 #pragma unroll
       for (int j = 0; j < kDotChunk; ++j)
@@ -88,7 +96,8 @@ __global__ void __launch_bounds__(kRedThreads) multi_dot_kernel(const double *__
 // w += sum_{i<k} sign * coef[i] * V_i ;  optionally out_norm2 = w . w afterwards
 __global__ void __launch_bounds__(kRedThreads) multi_axpy_kernel(const double *__restrict__ V, int64_t ld, int k,
                                                                  const double *__restrict__ coef, double sign,
-                                                                 double *__restrict__ w, int64_t n, int with_norm,
+                                                                 double *__restrict__ w, int64_t n, int64_t n1,
+                                                                 int64_t gap, int64_t n_norm, int with_norm,
                                                                  double *__restrict__ out_norm2, double *partials,
                                                                  unsigned *counter) {
   __shared__ double s_coef[kMaxDots];
@@ -97,12 +106,13 @@ __global__ void __launch_bounds__(kRedThreads) multi_axpy_kernel(const double *_
   for (int i = threadIdx.x; i < k; i += blockDim.x) s_coef[i] = sign * coef[i];
   __syncthreads();
   double nrm[1] = {0.0};
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = active_index(t, n1, gap);
     double a = w[e];
 #pragma unroll 4
     for (int i = 0; i < k; ++i) a += s_coef[i] * V[(int64_t)i * ld + e];
     w[e] = a;
-    nrm[0] += a * a;
+    if (t < n_norm) nrm[0] += a * a;  // the replicated part is counted on one rank only
   }
   if (!with_norm) return;
   block_reduce<1>(nrm, smem);

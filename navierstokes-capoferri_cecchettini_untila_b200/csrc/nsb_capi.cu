@@ -6,12 +6,18 @@
 //
 // Host code here only sequences kernels and runs the (restart x restart)
 // Hessenberg/Givens recurrence of GMRES; all O(N) work is on the device.
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is loaded with dlopen when a communicator is requested
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 
+#include <memory>
+
+#include "amg.cuh"
 #include "assemble.cuh"
 #include "common.cuh"
 #include "forces.cuh"
@@ -69,6 +75,26 @@ struct nsb_ctx {
   double t_ms[4] = {0, 0, 0, 0};
   DevBuf<char> flush;
   int spmv_L = 16;
+  // ---- domain decomposition (one process per GPU) ----
+  // Velocity rows are distributed: local nodes [0,n_own) are owned, [n_own,n_own+n_ghost) are
+  // ghosts refreshed by halo exchange.  Pressure vectors and S are replicated; this rank owns the
+  // pressure rows [p_begin, p_begin+n_p_own).  A vector is laid out [u owned | u ghost | p]:
+  // n_u = dim*n_own, n_uloc = dim*(n_own+n_ghost), N = n_uloc + n_p.  Single GPU: no ghosts.
+  int rank = 0, nranks = 1;
+  uint32_t n_own_nodes = 0, n_ghost_nodes = 0, p_begin = 0, n_p_own = 0;
+  int64_t n_uloc = 0;
+  std::vector<uint32_t> p_offsets;  // nranks+1
+  std::vector<int> neighbors;
+  std::vector<int64_t> send_ptr, recv_ptr;
+  DevBuf<uint32_t> send_idx;
+  DevBuf<double> send_buf;
+  ncclComm_t comm = nullptr;
+  DevBuf<double> a10t;  // A10^T values on the pattern of A01
+  // ---- Schur solve: 0 = single-level Chebyshev polynomial, 1 = multilevel V-cycle (amg.cuh) ----
+  int schur_mode = 1, amg_nu = 2, amg_max_agg = 8, amg_cycles = 1, amg_coarse_sweeps = 16;
+  double amg_theta = 0.08, amg_omega = 1.5, amg_smooth_ratio = 4.0, amg_coarse_ratio = 60.0;
+  std::vector<std::unique_ptr<AmgLevel>> amg;
+  bool amg_built = false;
 };
 
 namespace {
@@ -111,6 +137,86 @@ inline unsigned blocks_for(int64_t n_threads, int block = 256) { return (unsigne
 
 void fs_apply(nsb_ctx *c, int mode, bool with_a01, const double *xu, const double *xp, const double *d, double *y);
 
+// ---- NCCL, resolved at run time so that single-GPU users need no NCCL at all ----
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi &nccl() {
+  static NcclApi api;
+  if (api.lib) return api;
+  for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+    api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) throw NcclError(std::string("cannot load libnccl.so.2: ") + dlerror());
+  auto sym = [&](const char *n) {
+    void *f = dlsym(api.lib, n);
+    if (!f) throw NcclError(std::string("libnccl lacks ") + n);
+    return f;
+  };
+  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+  api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+  api.Send = (decltype(api.Send))sym("ncclSend");
+  api.Recv = (decltype(api.Recv))sym("ncclRecv");
+  api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+  api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  return api;
+}
+#define NSB_NCCL(call)                                                                       \
+  do {                                                                                       \
+    ncclResult_t r_ = (call);                                                                \
+    if (r_ != ncclSuccess) throw NcclError(std::string(#call) + ": " + nccl().GetErrorString(r_)); \
+  } while (0)
+
+// sum over ranks of `count` doubles, in place (dot products, norms, force integrals, S values)
+void allreduce_sum(nsb_ctx *c, double *buf, size_t count) {
+  if (c->nranks == 1) return;
+  NSB_NCCL(nccl().AllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->stream));
+}
+
+// Refresh the velocity ghosts of x from their owners (Epetra Import of the
+// reference's vmult; `solution = solution_owned`, reference :395).
+void halo_exchange(nsb_ctx *c, double *x) {
+  if (c->nranks == 1 || c->neighbors.empty()) return;
+  const int d = c->dim;
+  const int64_t ns = c->send_ptr.back();
+  if (ns > 0)
+    NSB_LAUNCH(c, halo_pack_kernel, blocks_for(ns * d), 256, ns, d, c->send_idx.p, x, c->send_buf.p);
+  NSB_NCCL(nccl().GroupStart());
+  for (size_t k = 0; k < c->neighbors.size(); ++k) {
+    const int64_t sb = c->send_ptr[k], sn = c->send_ptr[k + 1] - sb, rb = c->recv_ptr[k], rn = c->recv_ptr[k + 1] - rb;
+    if (sn > 0) NSB_NCCL(nccl().Send(c->send_buf.p + sb * d, (size_t)sn * d, ncclDouble, c->neighbors[k], c->comm, c->stream));
+    if (rn > 0)
+      NSB_NCCL(nccl().Recv(x + (int64_t)c->n_u + rb * d, (size_t)rn * d, ncclDouble, c->neighbors[k], c->comm, c->stream));
+  }
+  NSB_NCCL(nccl().GroupEnd());
+}
+
+// Make a pressure vector whose owned rows were just computed identical on all ranks.
+void allgather_p(nsb_ctx *c, double *yp) {
+  if (c->nranks == 1) return;
+  NSB_NCCL(nccl().GroupStart());
+  for (int r = 0; r < c->nranks; ++r) {
+    const size_t cnt = c->p_offsets[r + 1] - c->p_offsets[r];
+    if (cnt) NSB_NCCL(nccl().Broadcast(yp + c->p_offsets[r], yp + c->p_offsets[r], cnt, ncclDouble, r, c->comm, c->stream));
+  }
+  NSB_NCCL(nccl().GroupEnd());
+}
+
 int pick_L(const CsrDev &A) {
   const double mean = A.n_rows ? (double)A.nnz / (double)A.n_rows : 0.0;
   return mean < 12 ? 4 : mean < 40 ? 8 : mean < 120 ? 16 : 32;
@@ -134,8 +240,10 @@ void spmv(nsb_ctx *c, const CsrDev &A, int mode, const double *x, const double *
 
 // y = A x on the compressed storage: velocity rows F_s (+A01), pressure rows A10
 void block_spmv(nsb_ctx *c, const double *x, double *y) {
-  fs_apply(c, 0, true, x, x + c->n_u, nullptr, y);
-  spmv(c, c->a10, 0, x, nullptr, nullptr, y + c->n_u);
+  halo_exchange(c, const_cast<double *>(x));
+  fs_apply(c, 0, true, x, x + c->n_uloc, nullptr, y);
+  spmv(c, c->a10, 0, x, nullptr, nullptr, y + c->n_uloc + c->p_begin);
+  allgather_p(c, y + c->n_uloc);
 }
 
 // same product on the canonical (reference) block CSR; needs the materialised A00
@@ -210,26 +318,40 @@ void cheb_solve(nsb_ctx *c, const CsrDev *M /* nullptr: the velocity block F */,
     const double rho_new = 1.0 / (2.0 * sigma - rho);
     if (M)
       cheb_sweep(c, *M, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta);
-    else
+    else {
+      halo_exchange(c, z);
       fs_cheb_sweep(c, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta);
+    }
     std::swap(z, zn);
     rho = rho_new;
   }
 }
 
-void multi_dot(nsb_ctx *c, const double *V, int64_t ld, int k, const double *w, int64_t n, bool with_self,
+// Which part of a vector a reduction runs over.  FULL: owned velocity dofs +
+// the replicated pressure part (counted on rank 0 only); U: owned velocity
+// dofs; P: a replicated pressure vector (no communication).
+enum class Part { FULL, U, P };
+
+void multi_dot(nsb_ctx *c, const double *V, int64_t ld, int k, const double *w, Part part, bool with_self,
                double *out) {
-  NSB_LAUNCH(c, multi_dot_kernel, kRedBlocks, kRedThreads, V, ld, k, w, n, with_self ? 1 : 0, out, c->partials.p,
-             c->counter.p);
-}
-void multi_axpy(nsb_ctx *c, const double *V, int64_t ld, int k, const double *coef, double sign, double *w,
-                int64_t n, bool with_norm, double *out_norm2) {
-  NSB_LAUNCH(c, multi_axpy_kernel, kRedBlocks, kRedThreads, V, ld, k, coef, sign, w, n, with_norm ? 1 : 0, out_norm2,
+  const int64_t nu = c->n_u, np = c->n_p;
+  const int64_t n = part == Part::FULL ? nu + (c->rank == 0 ? np : 0) : part == Part::U ? nu : np;
+  const int64_t n1 = part == Part::P ? np : nu, gap = part == Part::FULL ? c->n_uloc - nu : 0;
+  NSB_LAUNCH(c, multi_dot_kernel, kRedBlocks, kRedThreads, V, ld, k, w, n, n1, gap, with_self ? 1 : 0, out,
              c->partials.p, c->counter.p);
+  if (part != Part::P) allreduce_sum(c, out, (size_t)k + (with_self ? 1 : 0));
+}
+// w += sign * V coef over the FULL part; optionally the squared norm of the result
+void multi_axpy(nsb_ctx *c, const double *V, int64_t ld, int k, const double *coef, double sign, double *w,
+                bool with_norm, double *out_norm2) {
+  const int64_t nu = c->n_u, np = c->n_p;
+  NSB_LAUNCH(c, multi_axpy_kernel, kRedBlocks, kRedThreads, V, ld, k, coef, sign, w, nu + np, nu, c->n_uloc - nu,
+             nu + (c->rank == 0 ? np : 0), with_norm ? 1 : 0, out_norm2, c->partials.p, c->counter.p);
+  if (with_norm) allreduce_sum(c, out_norm2, 1);
 }
 
-double norm2_host(nsb_ctx *c, const double *v, int64_t n) {
-  multi_dot(c, nullptr, 0, 0, v, n, true, c->hdev.p);
+double norm2_host(nsb_ctx *c, const double *v, Part part) {
+  multi_dot(c, nullptr, 0, 0, v, part, true, c->hdev.p);
   double h;
   NSB_CUDA(cudaMemcpyAsync(&h, c->hdev.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   NSB_CUDA(cudaStreamSynchronize(c->stream));
@@ -244,15 +366,18 @@ __global__ void eig_seed_kernel(int64_t n, double *v) {
 // lambda_max(D^-1 M) by power iteration, warm-started from `v`
 double power_lmax(nsb_ctx *c, const CsrDev *M /* nullptr: F */, const double *dinv, double *v, double *w, int iters) {
   const int64_t n = M ? M->n_rows : (int64_t)c->n_u;
+  const Part part = M ? Part::P : Part::U;
   double *h = c->hdev.p;
-  multi_dot(c, nullptr, 0, 0, v, n, true, h);
+  multi_dot(c, nullptr, 0, 0, v, part, true, h);
   NSB_LAUNCH(c, normalize_kernel, kRedBlocks, 256, n, h, v, v);
   for (int i = 0; i < iters; ++i) {
     if (M)
       spmv(c, *M, 3, v, nullptr, dinv, w);
-    else
+    else {
+      halo_exchange(c, v);
       fs_apply(c, 3, false, v, nullptr, dinv, w);
-    multi_dot(c, nullptr, 0, 0, w, n, true, h);
+    }
+    multi_dot(c, nullptr, 0, 0, w, part, true, h);
     NSB_LAUNCH(c, normalize_kernel, kRedBlocks, 256, n, h, w, v);
   }
   double n2;
@@ -341,8 +466,10 @@ void finalize_setup(nsb_ctx *c) {
   if (c->finalized) return;
   if (!c->have_mesh || !c->have_dofs || !c->fs.have || !c->a01.have || !c->a10.have)
     throw ArgError("setup incomplete: need nsb_set_mesh, nsb_set_dofs and the A00/A01/A10 patterns");
-  if (c->fs.n_rows * c->dim != c->n_u || c->a01.n_rows != c->n_u || c->a10.n_rows != c->n_p)
-    throw ArgError("pattern sizes do not match n_u/n_p");
+  if (c->fs.n_rows * c->dim != c->n_u || c->a01.n_rows != c->n_u || c->a10.n_rows != c->n_p_own)
+    throw ArgError("pattern sizes do not match the owned velocity / pressure rows");
+  if (c->nranks > 1 && !c->comm) throw ArgError("distributed setup needs nsb_comm_init before nsb_finalize_setup");
+  if (c->nranks > 1 && !c->s.have) throw ArgError("distributed setup needs the pattern of S (nsb_set_pattern(NSB_S))");
   if (!c->have_quad) {
     if (!fill_fe_tables(c->dim, c->quad_rule, c->fe_host)) throw ArgError("bad quadrature rule");
     c->fe.upload(&c->fe_host, 1, c->stream, &c->dev_bytes);
@@ -361,11 +488,11 @@ void finalize_setup(nsb_ctx *c) {
   if (c->dim == 2)
     NSB_LAUNCH(c, build_slots_kernel<2>, blocks_for(c->n_cells * per), 256, c->n_cells, c->cell_nodes.p,
                c->cell_pverts.p, c->fs.view(), c->a01.view(), c->a10.view(), c->slot00.p, c->slot01.p, c->slot10.p,
-               c->errflag.p);
+               c->p_begin, c->errflag.p);
   else
     NSB_LAUNCH(c, build_slots_kernel<3>, blocks_for(c->n_cells * per), 256, c->n_cells, c->cell_nodes.p,
                c->cell_pverts.p, c->fs.view(), c->a01.view(), c->a10.view(), c->slot00.p, c->slot01.p, c->slot10.p,
-               c->errflag.p);
+               c->p_begin, c->errflag.p);
   c->diagF.alloc((size_t)c->fs.n_rows, &c->dev_bytes);
   c->diagS.alloc(c->n_p, &c->dev_bytes);
   NSB_LAUNCH(c, diag_positions_kernel, blocks_for(c->fs.n_rows), 256, c->fs.view(), c->diagF.p, c->errflag.p);
@@ -387,16 +514,17 @@ void finalize_setup(nsb_ctx *c) {
   dz(c->coef, kMaxDots);
   c->counter.alloc(1, &c->dev_bytes);
   c->counter.zero(c->stream);
-  dz(c->vec0, c->n_u);
+  dz(c->a10t, (size_t)c->a01.nnz);
+  dz(c->vec0, c->n_uloc);  // velocity work vectors carry the ghost slots: they are SpMV inputs
   dz(c->vec1, c->n_p);
-  dz(c->chd_u, c->n_u);
-  dz(c->chz_u, c->n_u);
+  dz(c->chd_u, c->n_uloc);
+  dz(c->chz_u, c->n_uloc);
   dz(c->chd_p, c->n_p);
   dz(c->chz_p, c->n_p);
   dz(c->chz_p2, c->n_p);
-  dz(c->eig_u, c->n_u);
+  dz(c->eig_u, c->n_uloc);
   dz(c->eig_p, c->n_p);
-  dz(c->eig_w, c->n_u);
+  dz(c->eig_w, std::max<int64_t>(c->n_uloc, c->n_p));
   dz(c->force_out, 2);
   NSB_LAUNCH(c, eig_seed_kernel, blocks_for(c->n_u), 256, (int64_t)c->n_u, c->eig_u.p);
   NSB_LAUNCH(c, eig_seed_kernel, blocks_for(c->n_p), 256, (int64_t)c->n_p, c->eig_p.p);
@@ -433,6 +561,10 @@ void assemble_launch(nsb_ctx *c) {
   A.fs_val = c->fs.val.p;
   A.val01 = c->a01.val.p;
   A.val10 = c->a10.val.p;
+  A.val10t = c->a10t.p;
+  A.n_own_nodes = c->n_own_nodes;
+  A.p_begin = c->p_begin;
+  A.n_p_own = c->n_p_own;
   A.rhs = c->rhs.p;
   A.sol = c->sol.p;
   A.fe = c->fe.p;
@@ -442,6 +574,7 @@ void assemble_launch(nsb_ctx *c) {
   c->fs.val.zero(c->stream);
   c->a01.val.zero(c->stream);
   c->a10.val.zero(c->stream);
+  c->a10t.zero(c->stream);
   c->rhs.zero(c->stream);
   const unsigned grid =
       (unsigned)std::min<int64_t>((c->n_cells + kAsmWarps - 1) / kAsmWarps, (int64_t)kNumSM * 8);
@@ -465,6 +598,111 @@ void assemble_launch(nsb_ctx *c) {
 }
 
 // ---- preconditioner -------------------------------------------------------
+// ---- multilevel Schur solve (amg.cuh) ---------------------------------------
+const CsrDev &amg_matrix(nsb_ctx *c, size_t l) { return l == 0 ? c->s : c->amg[l]->M; }
+const double *amg_dinv(nsb_ctx *c, size_t l) { return l == 0 ? c->dis.p : c->amg[l]->dinv.p; }
+
+// aggregation hierarchy from the first assembled S (host, once; identical on all ranks because S is)
+void amg_build(nsb_ctx *c) {
+  HostCsr M;
+  M.n = c->s.n_rows;
+  M.rowptr.resize((size_t)M.n + 1);
+  M.colind.resize((size_t)c->s.nnz);
+  M.val.resize((size_t)c->s.nnz);
+  c->s.rowptr.download(M.rowptr.data(), c->stream);
+  c->s.colind.download(M.colind.data(), c->stream);
+  c->s.val.download(M.val.data(), c->stream);
+  c->amg.clear();
+  auto add_level = [&](int64_t n) {
+    c->amg.emplace_back(new AmgLevel);
+    AmgLevel &L = *c->amg.back();
+    L.n = n;
+    for (DevBuf<double> *b : {&L.b, &L.z0, &L.z1, &L.d, &L.r, &L.eig}) {
+      b->alloc((size_t)n, &c->dev_bytes);
+      b->zero(c->stream);
+    }
+    NSB_LAUNCH(c, eig_seed_kernel, blocks_for(n), 256, n, L.eig.p);
+    return &L;
+  };
+  AmgLevel *L = add_level(M.n);
+  while (M.n > 64 && c->amg.size() < 16) {
+    // the threshold is halved per level: Galerkin coarse operators have relatively weaker couplings
+    HostCoarsening C = coarsen(M, c->amg_theta * std::pow(0.5, (double)(c->amg.size() - 1)), c->amg_max_agg);
+    if (C.coarse.n >= 0.9 * M.n) break;  // coarsening stalled
+    L->agg.upload(C.agg.data(), C.agg.size(), c->stream, &c->dev_bytes);
+    L->agg_ptr.upload(C.agg_ptr.data(), C.agg_ptr.size(), c->stream, &c->dev_bytes);
+    L->agg_idx.upload(C.agg_idx.data(), C.agg_idx.size(), c->stream, &c->dev_bytes);
+    L->pos.upload(C.pos.data(), C.pos.size(), c->stream, &c->dev_bytes);
+    AmgLevel *Lc = add_level(C.coarse.n);
+    upload_pattern(c, Lc->M, C.coarse.n, C.coarse.n, C.coarse.rowptr.data(), C.coarse.colind.data());
+    Lc->dinv.alloc((size_t)C.coarse.n, &c->dev_bytes);
+    Lc->diag.alloc((size_t)C.coarse.n, &c->dev_bytes);
+    NSB_LAUNCH(c, diag_positions_kernel, blocks_for(C.coarse.n), 256, Lc->M.view(), Lc->diag.p, c->errflag.p);
+    M = std::move(C.coarse);
+    L = Lc;
+  }
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  c->amg_built = true;
+}
+
+// per step: Galerkin coarse operators, inverse diagonals and lambda_max of every level
+void amg_numeric(nsb_ctx *c) {
+  for (size_t l = 0; l < c->amg.size(); ++l) {
+    AmgLevel &L = *c->amg[l];
+    const CsrDev &M = amg_matrix(c, l);
+    if (l + 1 < c->amg.size()) {
+      AmgLevel &Lc = *c->amg[l + 1];
+      Lc.M.val.zero(c->stream);
+      NSB_LAUNCH(c, galerkin_sum_kernel, blocks_for(M.nnz), 256, M.nnz, M.val.p, L.pos.p, Lc.M.val.p);
+      NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(Lc.n), 256, Lc.n, 1, Lc.M.val.p, Lc.diag.p, Lc.dinv.p);
+    }
+    L.lmax = 1.05 * power_lmax(c, &M, amg_dinv(c, l), L.eig.p, L.r.p, L.eig_warm ? 5 : 25);
+    L.eig_warm = true;
+  }
+}
+
+// k Chebyshev-Jacobi sweeps on M z = b.  z_init == nullptr: zero initial guess;
+// otherwise z_init must be za or zb.  Returns the buffer that holds the result.
+double *cheb_smooth(nsb_ctx *c, const CsrDev &M, const double *dinv, const double *b, double *z_init, double *za,
+                    double *zb, double *d, int k, double lmax, double ratio) {
+  const int64_t n = M.n_rows;
+  const double lmin = lmax / ratio, theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  double *z, *zn;
+  if (!z_init) {
+    z = za;
+    zn = zb;
+    NSB_LAUNCH(c, cheb_first_kernel, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, z);
+  } else {
+    z = z_init == za ? zb : za;
+    zn = z_init;
+    cheb_sweep(c, M, dinv, b, z_init, d, z, 0.0, 1.0 / theta);  // d = Dinv (b - M z)/theta, z = z_init + d
+  }
+  double rho = 1.0 / sigma;
+  for (int i = 1; i < k; ++i) {
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    cheb_sweep(c, M, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta);
+    std::swap(z, zn);
+    rho = rho_new;
+  }
+  return z;
+}
+
+// one V-cycle on level l for M_l z = b; returns the buffer holding z
+double *amg_vcycle(nsb_ctx *c, size_t l, const double *b) {
+  AmgLevel &L = *c->amg[l];
+  const CsrDev &M = amg_matrix(c, l);
+  const double *dinv = amg_dinv(c, l);
+  if (l + 1 == c->amg.size())
+    return cheb_smooth(c, M, dinv, b, nullptr, L.z0.p, L.z1.p, L.d.p, c->amg_coarse_sweeps, L.lmax, c->amg_coarse_ratio);
+  double *z = cheb_smooth(c, M, dinv, b, nullptr, L.z0.p, L.z1.p, L.d.p, c->amg_nu, L.lmax, c->amg_smooth_ratio);
+  spmv(c, M, 1, z, b, nullptr, L.r.p);
+  AmgLevel &Lc = *c->amg[l + 1];
+  NSB_LAUNCH(c, restrict_kernel, blocks_for(Lc.n), 256, Lc.n, L.agg_ptr.p, L.agg_idx.p, L.r.p, Lc.b.p);
+  const double *ec = amg_vcycle(c, l + 1, Lc.b.p);
+  NSB_LAUNCH(c, prolong_add_kernel, blocks_for(L.n), 256, L.n, L.agg.p, ec, c->amg_omega, z);
+  return cheb_smooth(c, M, dinv, b, z, L.z0.p, L.z1.p, L.d.p, c->amg_nu, L.lmax, c->amg_smooth_ratio);
+}
+
 // Default inner-sweep parameters.  F = M/dt + nu K + C is mass dominated for
 // the benchmark time steps: a degree-3 polynomial on [lmax/6, lmax] reaches the
 // reference's 1e-2 inner tolerance.  S = B D^-1 Bt behaves like a Laplacian on
@@ -475,7 +713,7 @@ void auto_inner(nsb_ctx *c) {
     c->sweepsF = 3;
     c->ratioF = 6.0;
   }
-  if (c->sweepsS <= 0) {
+  if (c->sweepsS <= 0 && c->schur_mode == 0) {
     const double np = (double)c->n_p;
     c->ratioS = std::max(30.0, (c->dim == 3 ? 1.7 : 0.35) * std::pow(np, 2.0 / c->dim));
     c->sweepsS = std::max(4, (int)std::lround(1.5 * std::sqrt(c->ratioS)));
@@ -489,12 +727,17 @@ void prec_init(nsb_ctx *c) {
              c->di.p);
   if (c->prec != NSB_PREC_ASIMPLE) return;
   c->s.val.zero(c->stream);
-  NSB_LAUNCH(c, schur_numeric_kernel, blocks_for((int64_t)c->n_p * 32), 256, c->a10.view(), c->a01.view(), c->di.p,
+  NSB_LAUNCH(c, schur_outer_kernel, blocks_for((int64_t)c->n_u * 32), 256, c->a01.view(), c->a10t.p, c->di.p,
              c->s.view());
+  allreduce_sum(c, c->s.val.p, (size_t)c->s.nnz);
   NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_p), 256, (int64_t)c->n_p, 1, c->s.val.p, c->diagS.p, c->dis.p);
   const int its = c->eig_warm ? 6 : 30;
   c->lamF = 1.05 * power_lmax(c, nullptr, c->di.p, c->eig_u.p, c->eig_w.p, its);
-  c->lamS = 1.05 * power_lmax(c, &c->s, c->dis.p, c->eig_p.p, c->eig_w.p, its);
+  if (c->schur_mode == 1) {
+    if (!c->amg_built) amg_build(c);
+    amg_numeric(c);
+  } else
+    c->lamS = 1.05 * power_lmax(c, &c->s, c->dis.p, c->eig_p.p, c->eig_w.p, its);
   c->eig_warm = true;
 }
 
@@ -502,7 +745,7 @@ void prec_init(nsb_ctx *c) {
 // replaced by Chebyshev-Jacobi polynomials of fixed degree (a linear,
 // stationary operator: no stale initial guesses).
 void prec_apply(nsb_ctx *c, const double *src, double *dst) {
-  const int64_t nu = c->n_u, np = c->n_p;
+  const int64_t np = c->n_p;
   if (c->prec == NSB_PREC_IDENTITY) {
     NSB_CUDA(cudaMemcpyAsync(dst, src, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return;
@@ -510,12 +753,27 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
   // vec0 ~= F^-1 src0                                   (:978-981)
   cheb_solve(c, nullptr, c->di.p, src, c->vec0.p, c->chz_u.p, c->chd_u.p, c->sweepsF, c->lamF, c->ratioF);
   // vec1 = src1 - B vec0                                 (:982-983)
-  spmv(c, c->a10, 1, c->vec0.p, src + nu, nullptr, c->vec1.p);
+  halo_exchange(c, c->vec0.p);
+  spmv(c, c->a10, 1, c->vec0.p, src + c->n_uloc + c->p_begin, nullptr, c->vec1.p + c->p_begin);
+  allgather_p(c, c->vec1.p);
   // dst1 ~= S^-1 vec1, then dst1 *= -1/alpha             (:986-990)
-  cheb_solve(c, &c->s, c->dis.p, c->vec1.p, c->chz_p2.p, c->chz_p.p, c->chd_p.p, c->sweepsS, c->lamS, c->ratioS);
-  NSB_LAUNCH(c, scale_kernel, blocks_for(np), 256, np, -1.0 / c->alpha, c->chz_p2.p, dst + nu);
+  const double *d1;
+  if (c->schur_mode == 1) {
+    d1 = amg_vcycle(c, 0, c->vec1.p);
+    for (int cyc = 1; cyc < c->amg_cycles; ++cyc) {  // further cycles on the residual equation
+      spmv(c, c->s, 1, d1, c->vec1.p, nullptr, c->chz_p.p);
+      NSB_CUDA(cudaMemcpyAsync(c->chz_p2.p, d1, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      const double *e = amg_vcycle(c, 0, c->chz_p.p);
+      NSB_LAUNCH(c, axpby_kernel, kRedBlocks, 256, np, 1.0, e, 1.0, c->chz_p2.p);
+      d1 = c->chz_p2.p;
+    }
+  } else {
+    cheb_solve(c, &c->s, c->dis.p, c->vec1.p, c->chz_p2.p, c->chz_p.p, c->chd_p.p, c->sweepsS, c->lamS, c->ratioS);
+    d1 = c->chz_p2.p;
+  }
+  NSB_LAUNCH(c, scale_kernel, blocks_for(np), 256, np, -1.0 / c->alpha, d1, dst + c->n_uloc);
   // dst0 = vec0 - Di .* (Bt dst1)                        (:992-994)
-  spmv(c, c->a01, 2, dst + nu, c->vec0.p, c->di.p, dst);
+  spmv(c, c->a01, 2, dst + c->n_uloc, c->vec0.p, c->di.p, dst);
 }
 
 // ---- GMRES, reference :348-350, 377 ---------------------------
@@ -542,7 +800,7 @@ int gmres_solve(nsb_ctx *c, double tol) {
     block_spmv(c, x, p);
     NSB_LAUNCH(c, axpby_kernel, kRedBlocks, 256, N, 1.0, b, -1.0, p);
     prec_apply(c, p, V);
-    double rho = norm2_host(c, V, N);
+    double rho = norm2_host(c, V, Part::FULL);
     iterate = check(rho);
     if (!iterate) break;
     gamma[0] = rho;
@@ -555,10 +813,10 @@ int gmres_solve(nsb_ctx *c, double tol) {
       prec_apply(c, p, vv);
       dim = j + 1;
       // CGS2: h = V^T vv; vv -= V h; h2 = V^T vv; vv -= V h2; s = ||vv||
-      multi_dot(c, V, N, dim, vv, N, false, hd);
-      multi_axpy(c, V, N, dim, hd, -1.0, vv, N, false, nullptr);
-      multi_dot(c, V, N, dim, vv, N, false, hd + kMaxDots);
-      multi_axpy(c, V, N, dim, hd + kMaxDots, -1.0, vv, N, true, hd + 2 * kMaxDots);
+      multi_dot(c, V, N, dim, vv, Part::FULL, false, hd);
+      multi_axpy(c, V, N, dim, hd, -1.0, vv, false, nullptr);
+      multi_dot(c, V, N, dim, vv, Part::FULL, false, hd + kMaxDots);
+      multi_axpy(c, V, N, dim, hd + kMaxDots, -1.0, vv, true, hd + 2 * kMaxDots);
       NSB_CUDA(cudaMemcpyAsync(h.data(), hd, sizeof(double) * dim, cudaMemcpyDeviceToHost, c->stream));
       NSB_CUDA(cudaMemcpyAsync(h2.data(), hd + kMaxDots, sizeof(double) * dim, cudaMemcpyDeviceToHost, c->stream));
       double s2;
@@ -590,7 +848,7 @@ int gmres_solve(nsb_ctx *c, double tol) {
     }
     if (dim > 0) {
       NSB_CUDA(cudaMemcpyAsync(c->coef.p, y.data(), sizeof(double) * dim, cudaMemcpyHostToDevice, c->stream));
-      multi_axpy(c, V, N, dim, c->coef.p, 1.0, x, N, false, nullptr);
+      multi_axpy(c, V, N, dim, c->coef.p, 1.0, x, false, nullptr);
       NSB_CUDA(cudaStreamSynchronize(c->stream));  // y is reused by the next cycle
     }
   } while (iterate);
@@ -646,6 +904,12 @@ void nsb_destroy(nsb_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm) {
+    try {
+      nccl().CommDestroy(c->comm);
+    } catch (...) {
+    }
+  }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   cudaStream_t s = c->stream;
@@ -673,6 +937,14 @@ int nsb_set_dofs(nsb_ctx *c, uint32_t n_u, uint32_t n_p, const uint32_t *cell_do
     c->n_u = n_u;
     c->n_p = n_p;
     c->N = (int64_t)n_u + n_p;
+    c->rank = 0;
+    c->nranks = 1;
+    c->n_own_nodes = n_u / c->dim;
+    c->n_ghost_nodes = 0;
+    c->p_begin = 0;
+    c->n_p_own = n_p;
+    c->n_uloc = n_u;
+    c->p_offsets = {0u, n_p};
     DevBuf<uint32_t> cd;
     cd.upload(cell_dofs, (size_t)c->n_cells * c->DPC, c->stream);
     c->cell_nodes.alloc((size_t)c->n_cells * c->NN, &c->dev_bytes);
@@ -686,6 +958,53 @@ int nsb_set_dofs(nsb_ctx *c, uint32_t n_u, uint32_t n_p, const uint32_t *cell_do
     check_errflag(c, "nsb_set_dofs");
     c->have_dofs = true;
     c->finalized = false;
+  });
+}
+
+int nsb_set_local_dofs(nsb_ctx *c, int rank, int n_ranks, uint32_t n_own_nodes, uint32_t n_ghost_nodes, uint32_t n_p,
+                       const uint32_t *p_offsets, const uint32_t *cell_nodes, const uint32_t *cell_pverts) {
+  return guarded(c, [&] {
+    if (!c->have_mesh) throw ArgError("nsb_set_local_dofs: call nsb_set_mesh first");
+    if (rank < 0 || rank >= n_ranks || !p_offsets || !cell_nodes || !cell_pverts || p_offsets[n_ranks] != n_p)
+      throw ArgError("nsb_set_local_dofs: bad arguments");
+    c->rank = rank;
+    c->nranks = n_ranks;
+    c->n_own_nodes = n_own_nodes;
+    c->n_ghost_nodes = n_ghost_nodes;
+    c->n_u = (uint32_t)c->dim * n_own_nodes;
+    c->n_uloc = (int64_t)c->dim * (n_own_nodes + n_ghost_nodes);
+    c->n_p = n_p;
+    c->p_offsets.assign(p_offsets, p_offsets + n_ranks + 1);
+    c->p_begin = p_offsets[rank];
+    c->n_p_own = p_offsets[rank + 1] - p_offsets[rank];
+    c->N = c->n_uloc + n_p;
+    c->cell_nodes.upload(cell_nodes, (size_t)c->n_cells * c->NN, c->stream, &c->dev_bytes);
+    c->cell_pverts.upload(cell_pverts, (size_t)c->n_cells * c->NV, c->stream, &c->dev_bytes);
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_dofs = true;
+    c->finalized = false;
+  });
+}
+
+int nsb_set_halo(nsb_ctx *c, int n_neighbors, const int32_t *neighbors, const int64_t *send_ptr,
+                 const uint32_t *send_idx, const int64_t *recv_ptr) {
+  return guarded(c, [&] {
+    if (!c->have_dofs) throw ArgError("nsb_set_halo: call nsb_set_local_dofs first");
+    if (n_neighbors < 0 || (n_neighbors > 0 && (!neighbors || !send_ptr || !recv_ptr)))
+      throw ArgError("nsb_set_halo: null input");
+    c->neighbors.assign(neighbors, neighbors + n_neighbors);
+    c->send_ptr.assign(send_ptr, send_ptr + n_neighbors + 1);
+    c->recv_ptr.assign(recv_ptr, recv_ptr + n_neighbors + 1);
+    if (n_neighbors == 0) {
+      c->send_ptr = {0};
+      c->recv_ptr = {0};
+    }
+    if (c->recv_ptr.back() != (int64_t)c->n_ghost_nodes) throw ArgError("nsb_set_halo: receive counts != ghost count");
+    for (int64_t i = 0; i < c->send_ptr.back(); ++i)
+      if (send_idx[i] >= c->n_own_nodes) throw ArgError("nsb_set_halo: send index is not an owned node");
+    c->send_idx.upload(send_idx, (size_t)c->send_ptr.back(), c->stream, &c->dev_bytes);
+    c->send_buf.alloc((size_t)c->send_ptr.back() * c->dim, &c->dev_bytes);
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
   });
 }
 
@@ -724,14 +1043,14 @@ int nsb_set_pattern(nsb_ctx *c, int block, int64_t n_rows, const int64_t *rowptr
         break;
       }
       case NSB_A01:
-        if (n_rows != nu) throw ArgError("A01 must have n_u rows");
+        if (n_rows != nu) throw ArgError("A01 must have n_u (owned) rows");
         upload_pattern(c, c->a01, nu, np, rowptr, colind);
         c->h_rp01.assign(rowptr, rowptr + n_rows + 1);
         c->h_ci01.assign(colind, colind + rowptr[n_rows]);
         break;
       case NSB_A10:
-        if (n_rows != np) throw ArgError("A10 must have n_p rows");
-        upload_pattern(c, c->a10, np, nu, rowptr, colind);
+        if (n_rows != (int64_t)c->n_p_own) throw ArgError("A10 must have one row per owned pressure dof");
+        upload_pattern(c, c->a10, n_rows, c->n_uloc, rowptr, colind);
         c->h_rp10.assign(rowptr, rowptr + n_rows + 1);
         c->h_ci10.assign(colind, colind + rowptr[n_rows]);
         break;
@@ -749,8 +1068,8 @@ int nsb_set_pattern(nsb_ctx *c, int block, int64_t n_rows, const int64_t *rowptr
 int nsb_set_node_pattern(nsb_ctx *c, int64_t n_nodes, const int64_t *rowptr, const uint32_t *colind) {
   return guarded(c, [&] {
     if (!c->have_dofs) throw ArgError("nsb_set_node_pattern: call nsb_set_dofs first");
-    if (n_nodes * c->dim != (int64_t)c->n_u) throw ArgError("nsb_set_node_pattern: n_nodes*dim != n_u");
-    upload_pattern(c, c->fs, n_nodes, n_nodes, rowptr, colind);
+    if (n_nodes * c->dim != (int64_t)c->n_u) throw ArgError("nsb_set_node_pattern: n_nodes*dim != n_u (owned rows)");
+    upload_pattern(c, c->fs, n_nodes, c->n_uloc / c->dim, rowptr, colind);
     c->a00.have = false;
     c->finalized = false;
   });
@@ -803,6 +1122,18 @@ int nsb_set_inner(nsb_ctx *c, int sweeps_F, double eig_ratio_F, int sweeps_S, do
     c->ratioF = eig_ratio_F;
     c->sweepsS = sweeps_S;
     c->ratioS = eig_ratio_S;
+  });
+}
+
+int nsb_set_schur_solver(nsb_ctx *c, int mode, int smoother_sweeps, double strength_theta, double omega, int cycles) {
+  return guarded(c, [&] {
+    if (mode != 0 && mode != 1) throw ArgError("nsb_set_schur_solver: mode must be 0 (polynomial) or 1 (multilevel)");
+    c->schur_mode = mode;
+    if (smoother_sweeps > 0) c->amg_nu = smoother_sweeps;
+    if (strength_theta > 0) c->amg_theta = strength_theta;
+    if (omega > 0) c->amg_omega = omega;
+    if (cycles > 0) c->amg_cycles = cycles;
+    c->amg_built = false;
   });
 }
 
@@ -880,11 +1211,12 @@ int nsb_solve_time_step(nsb_ctx *c, int *iters, double *t_prec, double *t_solve)
   return guarded(c, [&] {
     if (!c->finalized) throw ArgError("nsb_solve_time_step: nothing assembled");
     auto t0 = std::chrono::high_resolution_clock::now();
-    const double tol = c->rtol * norm2_host(c, c->rhs.p, c->N);  // reference :348
+    const double tol = c->rtol * norm2_host(c, c->rhs.p, Part::FULL);  // reference :348
     prec_init(c);                                                 // reference :355-361
     NSB_CUDA(cudaStreamSynchronize(c->stream));
     auto t1 = std::chrono::high_resolution_clock::now();
     const int its = gmres_solve(c, tol);  // reference :377
+    halo_exchange(c, c->sol.p);           // solution = solution_owned (ghost import), reference :395
     NSB_CUDA(cudaStreamSynchronize(c->stream));
     auto t2 = std::chrono::high_resolution_clock::now();
     const double tp = std::chrono::duration<double>(t1 - t0).count(), ts = std::chrono::duration<double>(t2 - t1).count();
@@ -914,6 +1246,7 @@ int nsb_compute_forces(nsb_ctx *c, double u_mean, double out[4]) {
                    c->cell_verts.p, c->cell_nodes.p, c->cell_pverts.p, c->sol.p, c->n_u, c->fe.p, c->nu,
                    c->force_out.p);
     }
+    allreduce_sum(c, c->force_out.p, 2);  // Utilities::MPI::sum, reference :908-909
     NSB_CUDA(cudaEventRecord(c->ev1, c->stream));
     double dl[2];
     c->force_out.download(dl, c->stream);
@@ -999,8 +1332,8 @@ int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
         case 2: prec_apply(c, c->rhs.p, c->V.p); break;
         case 3:
           c->s.val.zero(c->stream);
-          NSB_LAUNCH(c, schur_numeric_kernel, blocks_for((int64_t)c->n_p * 32), 256, c->a10.view(), c->a01.view(),
-                     c->di.p, c->s.view());
+          NSB_LAUNCH(c, schur_outer_kernel, blocks_for((int64_t)c->n_u * 32), 256, c->a01.view(), c->a10t.p, c->di.p,
+                     c->s.view());
           break;
         case 4: fs_cheb_sweep(c, c->di.p, c->rhs.p, c->vec0.p, c->chd_u.p, c->chz_u.p, 0.5, 0.5); break;
         case 6: cheb_sweep(c, c->s, c->dis.p, c->vec1.p, c->chz_p.p, c->chd_p.p, c->chz_p2.p, 0.5, 0.5); break;
@@ -1049,15 +1382,28 @@ void nsb_free_pinned(void *p) {
 }
 
 int nsb_comm_unique_id(char id[128]) {
-  (void)id;
-  return NSB_ENCCL;
+  try {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId u;
+    if (nccl().GetUniqueId(&u) != ncclSuccess) return NSB_ENCCL;
+    std::memcpy(id, &u, 128);
+    return NSB_OK;
+  } catch (...) {
+    return NSB_ENCCL;
+  }
 }
 int nsb_comm_init(nsb_ctx *c, int rank, int n_ranks, const char id[128]) {
-  (void)rank;
-  (void)n_ranks;
-  (void)id;
-  if (c) c->err = "multi-GPU communicator not built in this revision";
-  return NSB_ENCCL;
+  return guarded(c, [&] {
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) throw ArgError("nsb_comm_init: bad rank");
+    if (c->have_dofs && (rank != c->rank || n_ranks != c->nranks))
+      throw ArgError("nsb_comm_init: rank/size differ from nsb_set_local_dofs");
+    if (n_ranks == 1) return;
+    ncclUniqueId u;
+    std::memcpy(&u, id, 128);
+    NSB_NCCL(nccl().CommInitRank(&c->comm, n_ranks, u, rank));
+    c->rank = rank;
+    c->nranks = n_ranks;
+  });
 }
 
 }  // extern "C"

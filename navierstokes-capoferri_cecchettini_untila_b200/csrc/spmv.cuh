@@ -204,33 +204,41 @@ __global__ void diag_inverse_kernel(int64_t n, int rep, const double *__restrict
   if (i < n) dinv[i] = 1.0 / val[diagpos[i / rep]];
 }
 
-// S = B diag(Di) Bt on the precomputed pattern of S (reference :956).  One warp
-// per row V of B = A10; lanes stride over the row's entries u and scatter
-// B[V,u] Di[u] Bt[u,W] into S[V,W] (position by binary search in row V of S).
-__global__ void __launch_bounds__(256) schur_numeric_kernel(CsrView B, CsrView Bt, const double *__restrict__ di,
-                                                            CsrView S) {
-  const int64_t V = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// S = B diag(Di) Bt on the precomputed pattern of S (reference :956), as a sum
+// of outer products over the velocity rows this rank owns:
+//   S[V,W] += B[V,u] Di[u] Bt[u,W],  B[V,u] = a10t[u,V] (pattern of row u of A01).
+// One warp per velocity dof; lanes stride over the (V,W) pairs of the row.  On
+// several GPUs every rank adds its owned rows and the values are all-reduced.
+__global__ void __launch_bounds__(256) schur_outer_kernel(CsrView Bt, const double *__restrict__ a10t,
+                                                          const double *__restrict__ di, CsrView S) {
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (V >= B.n_rows) return;
-  const int64_t sb = S.rowptr[V], se = S.rowptr[V + 1];
-  for (int64_t k = B.rowptr[V] + lane; k < B.rowptr[V + 1]; k += 32) {
-    const uint32_t u = B.colind[k];
-    const double coef = B.val[k] * di[u];
-    for (int64_t kk = Bt.rowptr[u]; kk < Bt.rowptr[u + 1]; ++kk) {
-      const double t = Bt.val[kk];
-      if (t == 0.0) continue;  // constrained rows of Bt are zero
-      const uint32_t W = Bt.colind[kk];
-      int64_t lo = sb, hi = se;
-      while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (S.colind[mid] < W)
-          lo = mid + 1;
-        else
-          hi = mid;
-      }
-      atomicAdd(S.val + lo, coef * t);
+  if (u >= Bt.n_rows) return;
+  const int64_t b = Bt.rowptr[u];
+  const int len = (int)(Bt.rowptr[u + 1] - b);
+  const double d = di[u];
+  for (int p = lane; p < len * len; p += 32) {
+    const int i = p / len, j = p % len;
+    const double t = Bt.val[b + j];
+    if (t == 0.0) continue;  // constrained rows of Bt are zero
+    const uint32_t V = Bt.colind[b + i], W = Bt.colind[b + j];
+    int64_t lo = S.rowptr[V], hi = S.rowptr[V + 1];
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (S.colind[mid] < W)
+        lo = mid + 1;
+      else
+        hi = mid;
     }
+    atomicAdd(S.val + lo, a10t[b + i] * d * t);
   }
+}
+
+// halo pack: buf[i][c] = x[dim*idx[i] + c]
+__global__ void halo_pack_kernel(int64_t n, int dim, const uint32_t *__restrict__ idx, const double *__restrict__ x,
+                                 double *__restrict__ buf) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n * dim) buf[t] = x[(int64_t)dim * idx[t / dim] + t % dim];
 }
 
 }  // namespace nsb

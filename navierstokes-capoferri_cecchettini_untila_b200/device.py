@@ -21,7 +21,7 @@ SYMBOLS = [
     "nsb_set_dirichlet", "nsb_scale_dirichlet", "nsb_set_force_faces", "nsb_assemble", "nsb_solve_time_step",
     "nsb_compute_forces", "nsb_get_matrix_values", "nsb_get_pattern", "nsb_nnz", "nsb_get_rhs", "nsb_vmult",
     "nsb_bench_kernel", "nsb_launch_count", "nsb_timers", "nsb_info", "nsb_alloc_pinned", "nsb_free_pinned",
-    "nsb_comm_unique_id", "nsb_comm_init",
+    "nsb_comm_unique_id", "nsb_comm_init", "nsb_set_local_dofs", "nsb_set_halo", "nsb_set_schur_solver",
 ]
 
 
@@ -52,6 +52,7 @@ def device_lib():
         L.nsb_set_bc_diag_mode.argtypes = [p, C.c_int]
         L.nsb_set_solver.argtypes = [p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int]
         L.nsb_set_inner.argtypes = [p, C.c_int, C.c_double, C.c_int, C.c_double]
+        L.nsb_set_schur_solver.argtypes = [p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
         L.nsb_set_solution.argtypes = [p, f64p]
         L.nsb_get_solution.argtypes = [p, f64p]
         L.nsb_set_dirichlet.argtypes = [p, C.c_int64, u32p, f64p]
@@ -76,6 +77,9 @@ def device_lib():
         L.nsb_free_pinned.argtypes = [C.c_void_p]
         L.nsb_comm_unique_id.argtypes = [C.c_char_p]
         L.nsb_comm_init.argtypes = [p, C.c_int, C.c_int, C.c_char_p]
+        i32p = C.POINTER(C.c_int32)
+        L.nsb_set_local_dofs.argtypes = [p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p, u32p]
+        L.nsb_set_halo.argtypes = [p, C.c_int, i32p, i64p, u32p, i64p]
         _lib = L
     return _lib
 
@@ -138,6 +142,50 @@ class Device:
         self.n_u, self.n_p = s["n_u"], s["n_p"]
         return self
 
+    @staticmethod
+    def make_unique_id() -> bytes:
+        """128-byte NCCL id; create on rank 0 and broadcast to the other ranks."""
+        buf = C.create_string_buffer(128)
+        if device_lib().nsb_comm_unique_id(buf) != 0:
+            raise DeviceError("nsb_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def load_local_problem(self, prob, loc, unique_id: bytes, quad_rule=QUAD_DEALII95):
+        """Distributed setup of rank ``loc.rank`` of ``loc.n_parts`` from a host
+        :class:`LocalProblem` (one process per GPU)."""
+        s = loc.sizes()
+        sz = prob.sizes()
+        xyz = prob.array("xyz")
+        cv, cn, cp = loc.array("cell_verts"), loc.array("cell_nodes"), loc.array("cell_pverts")
+        self._chk(self.L.nsb_set_mesh(self.h, sz["n_verts"], _p(xyz, C.c_double), s["n_local_cells"],
+                                      _p(cv, C.c_uint32)))
+        po = loc.array("p_offset")
+        self._chk(self.L.nsb_set_local_dofs(self.h, loc.rank, loc.n_parts, s["n_own"], s["n_ghost"], s["n_p"],
+                                            _p(po, C.c_uint32), _p(cn, C.c_uint32), _p(cp, C.c_uint32)))
+        nb, sp_, si, rp_ = (loc.array(k) for k in ("neighbors", "send_ptr", "send_idx", "recv_ptr"))
+        self._chk(self.L.nsb_set_halo(self.h, nb.size, _p(nb, C.c_int32), _p(sp_, C.c_int64), _p(si, C.c_uint32),
+                                      _p(rp_, C.c_int64)))
+        self._chk(self.L.nsb_comm_init(self.h, loc.rank, loc.n_parts, unique_id))
+        rp, ci = loc.array("fs.rowptr"), loc.array("fs.colind")
+        self._chk(self.L.nsb_set_node_pattern(self.h, rp.size - 1, _p(rp, C.c_int64), _p(ci, C.c_uint32)))
+        for blk, name in ((A01, "a01"), (A10, "a10"), (S, "s")):
+            rp, ci = loc.array(name + ".rowptr"), loc.array(name + ".colind")
+            self._chk(self.L.nsb_set_pattern(self.h, blk, rp.size - 1, _p(rp, C.c_int64), _p(ci, C.c_uint32)))
+        self._chk(self.L.nsb_set_quadrature(self.h, quad_rule))
+        dim = self.dim
+        bn = loc.array("bc_nodes")
+        dofs = (dim * bn[:, None] + np.arange(dim, dtype=np.uint32)[None, :]).astype(np.uint32).ravel()
+        self.set_dirichlet(dofs, loc.array("bc_values"))
+        fc, fn, fm = loc.array("ff.cell"), loc.array("ff.normal"), loc.array("ff.measure")
+        self._chk(self.L.nsb_set_force_faces(self.h, fc.size, _p(fc, C.c_uint32), _p(fn, C.c_double),
+                                             _p(fm, C.c_double)))
+        self._chk(self.L.nsb_finalize_setup(self.h))
+        self.n_u = dim * s["n_own"]
+        self.n_uloc = dim * (s["n_own"] + s["n_ghost"])
+        self.n_p = s["n_p"]
+        self.N = self.n_uloc + self.n_p
+        return self
+
     def set_params(self, deltat, nu):
         self._chk(self.L.nsb_set_params(self.h, deltat, nu))
 
@@ -149,6 +197,9 @@ class Device:
 
     def set_inner(self, sweeps_F, eig_ratio_F, sweeps_S, eig_ratio_S):
         self._chk(self.L.nsb_set_inner(self.h, sweeps_F, eig_ratio_F, sweeps_S, eig_ratio_S))
+
+    def set_schur_solver(self, mode=1, smoother_sweeps=0, theta=0.0, omega=0.0, cycles=0):
+        self._chk(self.L.nsb_set_schur_solver(self.h, mode, smoother_sweeps, theta, omega, cycles))
 
     def set_dirichlet(self, dofs, values):
         dofs = np.ascontiguousarray(dofs, np.uint32)

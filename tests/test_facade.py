@@ -22,7 +22,7 @@ def test_reference_drivers_compile_unmodified_against_facade(pkg, tmp_path, case
     src = glob.glob(os.path.join(REF, "tests", case, "src", "*.cpp"))
     assert len(src) == 1
     out = str(tmp_path / "drv")
-    cmd = ["/usr/bin/g++", "-O0", "-std=c++17", "-fopenmp", f"-DDIM={dim}", "-I" + os.path.join(PKG_DIR, "host"),
+    cmd = ["/usr/bin/g++", "-O0", "-std=c++17", "-fopenmp", f"-DDIM={dim}", "-DNS_INPUT=", "-I" + os.path.join(PKG_DIR, "host"),
            "-I" + os.path.join(ROOT, "include"), "-o", out, src[0], os.path.join(PKG_DIR, "host", "NavierStokes.cpp"),
            "-L" + PKG_DIR, "-lnsb_host", "-lnsb", "-Wl,-rpath," + PKG_DIR]
     r = subprocess.run(cmd, capture_output=True, text=True)
