@@ -289,12 +289,12 @@ def main():
     sweep_gbs = sweep_bytes(info, dim) * gb / (ms_sweep * 1e-3)
     sweep_s_gbs = sweep_s_bytes(info) * gb / (ms_sweep_s * 1e-3)
     asm_gbs = assembly_bytes(info, dim) * gb / (ms_asm * 1e-3)
-    # share of one outer GMRES iteration: (kF-1) F sweeps, (kS-1) S sweeps, one block product
-    kF_eff = int(kF) if int(kF) > 0 else 3
-    kS_eff = int(kS) if int(kS) > 0 else max(4, round(1.5 * (max(30.0, 1.7 * info["n_p"] ** (2.0 / 3))) ** 0.5))
+    # share of one outer GMRES iteration: (kF-1) F sweeps, the fine-level S sweeps, one block product
+    info2 = dev.info()
+    kF_eff, kS_eff = info2["sweeps_F"], info2["sweeps_S"] + (1 if info2["schur_mode"] == 1 else 0)
     shares = {"fs_cheb_sweep_kernel (Jacobi-type sweep on F, node-block CSR)": ((kF_eff - 1) * ms_sweep, sweep_gbs,
                                                                                sweep_bytes(info, dim), ms_sweep),
-              "cheb_sweep_kernel (Jacobi-type sweep on S)": ((kS_eff - 1) * ms_sweep_s, sweep_s_gbs,
+              "cheb_sweep_kernel (Jacobi-type sweep on S)": (max(kS_eff - 1, 1) * ms_sweep_s, sweep_s_gbs,
                                                              sweep_s_bytes(info), ms_sweep_s),
               "fs_apply_kernel + spmv_kernel (block product y = A x)": (ms_spmv, spmv_gbs, spmv_bytes(info, dim),
                                                                        ms_spmv)}
@@ -311,7 +311,7 @@ def main():
             "assembly_dofs_per_s": N / (ms_asm * 1e-3), "assembly_gbs": asm_gbs, "assembly_ms": ms_asm,
             "spmv_gbs": spmv_gbs, "spmv_frac_of_hbm": spmv_gbs / hbm_peak, "spmv_ms": ms_spmv,
             "sweep_F_gbs": sweep_gbs, "sweep_F_ms": ms_sweep, "sweep_S_gbs": sweep_s_gbs, "sweep_S_ms": ms_sweep_s,
-            "schur_ms": ms_schur,
+            "schur_ms": ms_schur, "sweeps_F": info2["sweeps_F"], "schur_levels": info2["schur_levels"],
             "spmv_canonical_gbs": (spmv_canonical_bytes(info) * gb / (ms_spmv_can * 1e-3)) if ms_spmv_can else None,
             "spmv_canonical_ms": ms_spmv_can,
             "prec_apply_ms": ms_prec, "cd": float(forces[2]), "cl": float(forces[3]),

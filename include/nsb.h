@@ -132,9 +132,11 @@ int nsb_bench_kernel(nsb_ctx *ctx, int which, int reps, double *ms_mean);
 int64_t nsb_launch_count(const nsb_ctx *ctx);
 /* timers of the last step in ms: [0] assemble, [1] prec init, [2] solve, [3] forces */
 int nsb_timers(const nsb_ctx *ctx, double out_ms[4]);
-/* info: [0] n_u [1] n_p [2] n_cells [3] nnz A00 [4] nnz A01 [5] nnz A10 [6] nnz S
- *       [7] n_q [8] device bytes allocated */
-int nsb_info(const nsb_ctx *ctx, int64_t out[9]);
+/* info: [0] n_u [1] n_p [2] n_cells [3] nnz A00 (canonical) [4] nnz A01 [5] nnz A10 [6] nnz S
+ *       [7] n_q [8] device bytes allocated [9] Chebyshev degree on F in effect
+ *       [10] fine-level S sweeps per preconditioner application [11] Schur solver mode
+ *       [12] number of levels of the Schur hierarchy */
+int nsb_info(const nsb_ctx *ctx, int64_t out[13]);
 
 /* pinned host memory for callers that want asynchronous copies */
 void *nsb_alloc_pinned(int64_t bytes);

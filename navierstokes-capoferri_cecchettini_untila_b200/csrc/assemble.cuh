@@ -360,6 +360,42 @@ __global__ void apply_dirichlet_kernel(int64_t n_bc_nodes, const uint32_t *__res
   }
 }
 
+// diagonal of the velocity mass matrix, M_AA = sum_cells |J| M^(a,a) (geometry only; computed once).
+// Used to choose the degree of the Chebyshev polynomial for F (see auto_inner in nsb_capi.cu).
+template <int DIM>
+__global__ void mass_diag_kernel(int64_t n_cells, const double *__restrict__ xyz,
+                                 const uint32_t *__restrict__ cell_verts, const uint32_t *__restrict__ cell_nodes,
+                                 uint32_t n_own_nodes, const FeTables *__restrict__ fe, double *mdiag) {
+  constexpr int NV = DIM + 1, NN = DIM == 2 ? 6 : 10;
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  double X[NV][DIM];
+  for (int a = 0; a < NV; ++a)
+    for (int r = 0; r < DIM; ++r) X[a][r] = xyz[(size_t)cell_verts[cell * NV + a] * DIM + r];
+  double det;
+  if constexpr (DIM == 2) {
+    det = (X[1][0] - X[0][0]) * (X[2][1] - X[0][1]) - (X[2][0] - X[0][0]) * (X[1][1] - X[0][1]);
+  } else {
+    double J[3][3];
+    for (int a = 0; a < 3; ++a)
+      for (int r = 0; r < 3; ++r) J[r][a] = X[a + 1][r] - X[0][r];
+    det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+          J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+  }
+  for (int a = 0; a < NN; ++a) {
+    const uint32_t node = cell_nodes[cell * NN + a];
+    if (node < n_own_nodes) atomicAdd(mdiag + node, fabs(det) * fe->mhat[a][a]);
+  }
+}
+
+// w[A] = sqrt( F_AA * dt / M_AA ): sum of squares = sum of the diagonal growth ratios
+__global__ void diag_ratio_kernel(int64_t n_nodes, const double *__restrict__ fs_val,
+                                  const int64_t *__restrict__ diagpos, const double *__restrict__ mdiag, double dt,
+                                  double *__restrict__ w) {
+  const int64_t A = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (A < n_nodes) w[A] = sqrt(fabs(fs_val[diagpos[A]]) * dt / mdiag[A]);
+}
+
 // canonical A00 values from F_s: val[rowptr(dim*A+c) + dim*k + c'] = (c == c') F_s[A,k]
 template <int DIM>
 __global__ void expand_values_kernel(int64_t n_nodes, const int64_t *__restrict__ nptr,

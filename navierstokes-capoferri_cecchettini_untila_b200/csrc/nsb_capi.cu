@@ -61,8 +61,11 @@ struct nsb_ctx {
   // parameters (NavierStokes.hpp:254-256, 306; NavierStokes.cpp:348, 972-973)
   double dt = 0.01, nu = 1e-3, alpha = 0.5, rtol = 1e-6;
   int restart = 28, max_it = 10000, prec = NSB_PREC_ASIMPLE;
-  int sweepsF = 0, sweepsS = 0;  // 0 = automatic (see auto_inner)
+  int sweepsF = 0, sweepsS = 0;  // user settings; 0 = automatic (see auto_inner)
   double ratioF = 0.0, ratioS = 0.0;
+  int kF = 3, kS = 20;           // values in effect for the current step
+  double rF = 6.0, rS = 300.0;
+  DevBuf<double> mdiag;          // diagonal of the velocity mass matrix (owned nodes)
   // Krylov work space
   DevBuf<double> V, tmpN, hdev, partials, coef;
   DevBuf<unsigned> counter;
@@ -333,8 +336,8 @@ void cheb_solve(nsb_ctx *c, const CsrDev *M /* nullptr: the velocity block F */,
 enum class Part { FULL, U, P };
 
 void multi_dot(nsb_ctx *c, const double *V, int64_t ld, int k, const double *w, Part part, bool with_self,
-               double *out) {
-  const int64_t nu = c->n_u, np = c->n_p;
+               double *out, int64_t n_replicated = -1 /* length of a Part::P vector, default n_p */) {
+  const int64_t nu = c->n_u, np = n_replicated >= 0 ? n_replicated : (int64_t)c->n_p;
   const int64_t n = part == Part::FULL ? nu + (c->rank == 0 ? np : 0) : part == Part::U ? nu : np;
   const int64_t n1 = part == Part::P ? np : nu, gap = part == Part::FULL ? c->n_uloc - nu : 0;
   NSB_LAUNCH(c, multi_dot_kernel, kRedBlocks, kRedThreads, V, ld, k, w, n, n1, gap, with_self ? 1 : 0, out,
@@ -368,7 +371,7 @@ double power_lmax(nsb_ctx *c, const CsrDev *M /* nullptr: F */, const double *di
   const int64_t n = M ? M->n_rows : (int64_t)c->n_u;
   const Part part = M ? Part::P : Part::U;
   double *h = c->hdev.p;
-  multi_dot(c, nullptr, 0, 0, v, part, true, h);
+  multi_dot(c, nullptr, 0, 0, v, part, true, h, n);
   NSB_LAUNCH(c, normalize_kernel, kRedBlocks, 256, n, h, v, v);
   for (int i = 0; i < iters; ++i) {
     if (M)
@@ -377,7 +380,7 @@ double power_lmax(nsb_ctx *c, const CsrDev *M /* nullptr: F */, const double *di
       halo_exchange(c, v);
       fs_apply(c, 3, false, v, nullptr, dinv, w);
     }
-    multi_dot(c, nullptr, 0, 0, w, part, true, h);
+    multi_dot(c, nullptr, 0, 0, w, part, true, h, n);
     NSB_LAUNCH(c, normalize_kernel, kRedBlocks, 256, n, h, w, v);
   }
   double n2;
@@ -526,6 +529,13 @@ void finalize_setup(nsb_ctx *c) {
   dz(c->eig_p, c->n_p);
   dz(c->eig_w, std::max<int64_t>(c->n_uloc, c->n_p));
   dz(c->force_out, 2);
+  dz(c->mdiag, (size_t)c->n_own_nodes);
+  if (c->dim == 2)
+    NSB_LAUNCH(c, mass_diag_kernel<2>, blocks_for(c->n_cells), 256, c->n_cells, c->xyz.p, c->cell_verts.p,
+               c->cell_nodes.p, c->n_own_nodes, c->fe.p, c->mdiag.p);
+  else
+    NSB_LAUNCH(c, mass_diag_kernel<3>, blocks_for(c->n_cells), 256, c->n_cells, c->xyz.p, c->cell_verts.p,
+               c->cell_nodes.p, c->n_own_nodes, c->fe.p, c->mdiag.p);
   NSB_LAUNCH(c, eig_seed_kernel, blocks_for(c->n_u), 256, (int64_t)c->n_u, c->eig_u.p);
   NSB_LAUNCH(c, eig_seed_kernel, blocks_for(c->n_p), 256, (int64_t)c->n_p, c->eig_p.p);
   const char *envL = std::getenv("NSB_SPMV_L");
@@ -703,20 +713,43 @@ double *amg_vcycle(nsb_ctx *c, size_t l, const double *b) {
   return cheb_smooth(c, M, dinv, b, z, L.z0.p, L.z1.p, L.d.p, c->amg_nu, L.lmax, c->amg_smooth_ratio);
 }
 
-// Default inner-sweep parameters.  F = M/dt + nu K + C is mass dominated for
-// the benchmark time steps: a degree-3 polynomial on [lmax/6, lmax] reaches the
-// reference's 1e-2 inner tolerance.  S = B D^-1 Bt behaves like a Laplacian on
-// the pressure mesh, cond(D_S^-1 S) ~ (L/h)^2 ~ n_p^(2/dim): the interval
-// ratio follows that estimate and the degree is 1.5 sqrt(ratio).
+// Inner-sweep parameters in effect for this step.
+// F = M/dt + nu K + C(u): with Jacobi scaling lambda_max(D^-1 F) stays ~2.5 and
+// lambda_min ~ lambda_min(D_M^-1 M) / gamma, gamma = mean_A F_AA / (M_AA/dt) >= 1
+// (gamma - 1 ~ nu dt / h^2 measures how far F is from its mass part), so the
+// condition number is ~7 gamma.  The polynomial degree grows like sqrt(gamma):
+// 3-4 on the mass-dominated benchmark meshes, 6-9 at 2-7 M DoFs -- the
+// fixed-cost analogue of the reference's "iterate to 1e-2" (reference :978).
+// S (single-level mode only): cond ~ (L/h)^2 ~ n_p^(2/dim).
 void auto_inner(nsb_ctx *c) {
-  if (c->sweepsF <= 0) {
-    c->sweepsF = 3;
-    c->ratioF = 6.0;
+  if (c->sweepsF > 0) {
+    c->kF = c->sweepsF;
+    c->rF = c->ratioF;
+  } else {
+    const int64_t nn = c->n_own_nodes;
+    NSB_LAUNCH(c, diag_ratio_kernel, blocks_for(nn), 256, nn, c->fs.val.p, c->diagF.p, c->mdiag.p, c->dt, c->eig_w.p);
+    multi_dot(c, nullptr, 0, 0, c->eig_w.p, Part::P, true, c->hdev.p, nn);
+    const double cnt = (double)nn;
+    NSB_CUDA(cudaMemcpyAsync(c->hdev.p + 1, &cnt, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    allreduce_sum(c, c->hdev.p, 2);
+    double h[2];
+    NSB_CUDA(cudaMemcpyAsync(h, c->hdev.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+    const double gamma = std::max(1.0, h[0] / h[1]);
+    // measured on B200 (3d-cylinder, h = 0.04 ... 0.0125): time per step is flat for degrees within
+    // +-2 of 0.55 sqrt(7 gamma); a higher degree buys fewer outer iterations at the same total cost
+    c->kF = std::min(16, std::max(3, (int)std::ceil(0.55 * std::sqrt(7.0 * gamma))));
+    c->rF = std::max(6.0, (c->kF / 1.25) * (c->kF / 1.25));
   }
-  if (c->sweepsS <= 0 && c->schur_mode == 0) {
-    const double np = (double)c->n_p;
-    c->ratioS = std::max(30.0, (c->dim == 3 ? 1.7 : 0.35) * std::pow(np, 2.0 / c->dim));
-    c->sweepsS = std::max(4, (int)std::lround(1.5 * std::sqrt(c->ratioS)));
+  if (c->schur_mode == 0) {
+    if (c->sweepsS > 0) {
+      c->kS = c->sweepsS;
+      c->rS = c->ratioS;
+    } else {
+      const double np = (double)c->n_p;
+      c->rS = std::max(30.0, (c->dim == 3 ? 1.7 : 0.35) * std::pow(np, 2.0 / c->dim));
+      c->kS = std::max(4, (int)std::lround(1.5 * std::sqrt(c->rS)));
+    }
   }
 }
 
@@ -751,7 +784,7 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
     return;
   }
   // vec0 ~= F^-1 src0                                   (:978-981)
-  cheb_solve(c, nullptr, c->di.p, src, c->vec0.p, c->chz_u.p, c->chd_u.p, c->sweepsF, c->lamF, c->ratioF);
+  cheb_solve(c, nullptr, c->di.p, src, c->vec0.p, c->chz_u.p, c->chd_u.p, c->kF, c->lamF, c->rF);
   // vec1 = src1 - B vec0                                 (:982-983)
   halo_exchange(c, c->vec0.p);
   spmv(c, c->a10, 1, c->vec0.p, src + c->n_uloc + c->p_begin, nullptr, c->vec1.p + c->p_begin);
@@ -768,7 +801,7 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
       d1 = c->chz_p2.p;
     }
   } else {
-    cheb_solve(c, &c->s, c->dis.p, c->vec1.p, c->chz_p2.p, c->chz_p.p, c->chd_p.p, c->sweepsS, c->lamS, c->ratioS);
+    cheb_solve(c, &c->s, c->dis.p, c->vec1.p, c->chz_p2.p, c->chz_p.p, c->chd_p.p, c->kS, c->lamS, c->rS);
     d1 = c->chz_p2.p;
   }
   NSB_LAUNCH(c, scale_kernel, blocks_for(np), 256, np, -1.0 / c->alpha, d1, dst + c->n_uloc);
@@ -1355,7 +1388,7 @@ int nsb_timers(const nsb_ctx *c, double out_ms[4]) {
   for (int i = 0; i < 4; ++i) out_ms[i] = c->t_ms[i];
   return NSB_OK;
 }
-int nsb_info(const nsb_ctx *c, int64_t out[9]) {
+int nsb_info(const nsb_ctx *c, int64_t out[13]) {
   if (!c) return NSB_EARG;
   out[0] = c->n_u;
   out[1] = c->n_p;
@@ -1366,6 +1399,10 @@ int nsb_info(const nsb_ctx *c, int64_t out[9]) {
   out[6] = c->s.nnz;
   out[7] = c->fe_host.nq;
   out[8] = c->dev_bytes;
+  out[9] = c->kF;
+  out[10] = c->schur_mode == 1 ? 2 * c->amg_nu * c->amg_cycles : c->kS;
+  out[11] = c->schur_mode;
+  out[12] = (int64_t)c->amg.size();
   return NSB_OK;
 }
 

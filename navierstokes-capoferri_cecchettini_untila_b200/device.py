@@ -274,7 +274,8 @@ class Device:
         return out
 
     def info(self):
-        out = (C.c_int64 * 9)()
+        out = (C.c_int64 * 13)()
         self._chk(self.L.nsb_info(self.h, out))
-        keys = ["n_u", "n_p", "n_cells", "nnz_a00", "nnz_a01", "nnz_a10", "nnz_s", "n_q", "device_bytes"]
+        keys = ["n_u", "n_p", "n_cells", "nnz_a00", "nnz_a01", "nnz_a10", "nnz_s", "n_q", "device_bytes", "sweeps_F",
+                "sweeps_S", "schur_mode", "schur_levels"]
         return dict(zip(keys, [int(v) for v in out]))
