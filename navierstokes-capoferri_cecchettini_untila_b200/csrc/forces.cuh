@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(128) forces_kernel(int64_t n_faces, const uint
                                                      const uint32_t *__restrict__ cell_verts,
                                                      const uint32_t *__restrict__ cell_nodes,
                                                      const uint32_t *__restrict__ cell_pverts,
-                                                     const double *__restrict__ sol, uint32_t n_u,
+                                                     const double *__restrict__ sol, int64_t p_offset /* start of the pressure part */,
                                                      const FeTables *__restrict__ fe, double nu,
                                                      double *__restrict__ out /* drag, lift */) {
   constexpr int NV = DIM + 1, NN = DIM == 2 ? 6 : 10;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) forces_kernel(int64_t n_faces, const uint
     const double meas = measure[f];
     for (int q = 0; q < fe->nqf; ++q) {
       double p = 0, ngt = 0;
-      for (int k = 0; k < NV; ++k) p += sol[n_u + cell_pverts[cell * NV + k]] * fe->psi[q][k];
+      for (int k = 0; k < NV; ++k) p += sol[p_offset + cell_pverts[cell * NV + k]] * fe->psi[q][k];
       for (int a = 0; a < NN; ++a) {
         double g[DIM];
         for (int c = 0; c < DIM; ++c) {

@@ -1272,11 +1272,11 @@ int nsb_compute_forces(nsb_ctx *c, double u_mean, double out[4]) {
       const unsigned grid = (unsigned)std::min<int64_t>((nf + 127) / 128, kNumSM * 4);
       if (c->dim == 2)
         NSB_LAUNCH(c, forces_kernel<2>, grid, 128, nf, c->ff_cell.p, c->ff_normal.p, c->ff_measure.p, c->xyz.p,
-                   c->cell_verts.p, c->cell_nodes.p, c->cell_pverts.p, c->sol.p, c->n_u, c->fe.p, c->nu,
+                   c->cell_verts.p, c->cell_nodes.p, c->cell_pverts.p, c->sol.p, c->n_uloc, c->fe.p, c->nu,
                    c->force_out.p);
       else
         NSB_LAUNCH(c, forces_kernel<3>, grid, 128, nf, c->ff_cell.p, c->ff_normal.p, c->ff_measure.p, c->xyz.p,
-                   c->cell_verts.p, c->cell_nodes.p, c->cell_pverts.p, c->sol.p, c->n_u, c->fe.p, c->nu,
+                   c->cell_verts.p, c->cell_nodes.p, c->cell_pverts.p, c->sol.p, c->n_uloc, c->fe.p, c->nu,
                    c->force_out.p);
     }
     allreduce_sum(c, c->force_out.p, 2);  // Utilities::MPI::sum, reference :908-909
