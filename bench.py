@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--mesh", default="3d-cylinder")
-    ap.add_argument("--h", type=float, default=float(os.environ.get("NSB_BENCH_H", "0.0125")),
+    ap.add_argument("--h", type=float, default=float(os.environ.get("NSB_BENCH_H", "0.011")),
                     help="target edge length of the mesh (0.011 ~ 10M DoFs)")
     ap.add_argument("--cpu-h", type=float, default=0.05, help="mesh of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -207,16 +207,26 @@ def main():
         print(json.dumps(line))
         return 0
 
-    if world > 1:
-        raise SystemExit("multi-GPU bench is not wired in this revision")
-
     # ---------------- native arm ----------------
+    dist = None
+    if world > 1:  # one process per GPU (torchrun); gloo carries the NCCL id, barriers and the max over ranks
+        import torch
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
     t_setup = time.perf_counter()
     prob = pkg.Problem.generate(a.mesh, a.h)
     prob.build(inlet=(pkg.INLET_PARABOLIC, U_M, H_CH, 0), expand_a00=False)
     sz = prob.sizes()
     dim = sz["dim"]
-    dev = pkg.Device(dim, local_rank).load_problem(prob, node_pattern=True)
+    loc = None
+    if world > 1:
+        prob.partition(world)  # same deterministic RCB partition on every rank
+        loc = pkg.LocalProblem(prob, world, rank)
+        ids = [pkg.Device.make_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        dev = pkg.Device(dim, local_rank).load_local_problem(prob, loc, ids[0])
+    else:
+        dev = pkg.Device(dim, local_rank).load_problem(prob, node_pattern=True)
     nu = prob.mean_velocity(0.0) * 0.4 / RE  # set_re_number, reference :332-341
     dev.set_params(DT, nu)
     dev.set_solver(1e-6, 28, 10000, a.alpha)
@@ -224,17 +234,35 @@ def main():
     sm = a.schur.split(",")
     dev.set_schur_solver(int(sm[0]), int(sm[1]), float(sm[2]), float(sm[3]), int(sm[4]))
     info = dev.info()
-    N = info["n_u"] + info["n_p"]
+    N = sz["n_u"] + sz["n_p"]      # global unknowns
+    N_loc = dev.N                  # this rank's vector (owned + ghost velocity, replicated pressure)
     t_setup = time.perf_counter() - t_setup
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     import ctypes as C
     L = dev.L
-    bc_dofs = np.array(prob.array("bc.dofs"))
-    pin_bc = L.nsb_alloc_pinned(8 * bc_dofs.size)
-    pin_sol = L.nsb_alloc_pinned(8 * N)
+    if loc is None:
+        bc_dofs = np.array(prob.array("bc.dofs"))
+        bc_vals = prob.array("bc.values")
+    else:
+        bn = loc.array("bc_nodes")
+        bc_dofs = (dim * bn[:, None] + np.arange(dim, dtype=np.uint32)[None, :]).astype(np.uint32).ravel()
+        bc_vals = loc.array("bc_values")
+    pin_bc = L.nsb_alloc_pinned(8 * max(bc_dofs.size, 1))
+    pin_sol = L.nsb_alloc_pinned(8 * N_loc)
     bc_host = np.frombuffer((C.c_char * (8 * bc_dofs.size)).from_address(pin_bc), dtype=np.float64)
-    sol_host = np.frombuffer((C.c_char * (8 * N)).from_address(pin_sol), dtype=np.float64)
-    bc_host[:] = prob.array("bc.values")
+    sol_host = np.frombuffer((C.c_char * (8 * N_loc)).from_address(pin_sol), dtype=np.float64)
+    bc_host[:] = bc_vals
 
     state = {"t": 0.0}
     iters, tasm, tprec, tsol = [], [], [], []
@@ -261,18 +289,22 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = dev.launch_count()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        forces = step(False)
-    ms_dev = 1e3 * (time.perf_counter() - t0) / a.steps
+        forces = step(False)   # every API call ends with a stream synchronise
+    barrier()
+    ms_dev = max_over_ranks(1e3 * (time.perf_counter() - t0) / a.steps)
     launches = dev.launch_count() - l0
     dev_stats = dict(iters=float(np.mean(iters)), asm=float(np.mean(tasm)), prec=float(np.mean(tprec)),
                      sol=float(np.mean(tsol)))
     # end to end through the C ABI with host buffers
+    barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         forces = step(True)
-    ms_e2e = 1e3 * (time.perf_counter() - t0) / a.steps
+    barrier()
+    ms_e2e = max_over_ranks(1e3 * (time.perf_counter() - t0) / a.steps)
     # kernel micro-benchmarks on the resident system (CUDA events on the ctx stream)
     reps = 20
     ms_spmv = dev.bench_kernel(5, reps)
@@ -281,7 +313,7 @@ def main():
     ms_asm = dev.bench_kernel(1, 5)
     ms_prec = dev.bench_kernel(2, 5)
     ms_schur = dev.bench_kernel(3, 5)
-    ms_spmv_can = dev.bench_kernel(0, reps) if a.canonical_spmv else None
+    ms_spmv_can = dev.bench_kernel(0, reps) if (a.canonical_spmv and world == 1) else None
     clocks = sampler.stop()
 
     gb = 1e-9
@@ -318,9 +350,18 @@ def main():
             "setup_s": t_setup, "device_bytes": info["device_bytes"],
             "roofline": roof, "clocks": clocks,
             "e2e": {"value": ms_e2e, "unit": "ms/step", "h2d_bytes_per_step": int(8 * bc_dofs.size + 4 * bc_dofs.size),
-                    "d2h_bytes_per_step": int(8 * N + 32)},
+                    "d2h_bytes_per_step": int(8 * N_loc + 32)},
             "gpu_launches": int(launches)}
-    if not a.no_cpu_baseline:
+    if world > 1:
+        line["n_dofs_local"] = N_loc
+        line["partition"] = "recursive coordinate bisection of the cells; velocity rows distributed, pressure replicated"
+    if rank != 0:
+        L.nsb_free_pinned(pin_bc)
+        L.nsb_free_pinned(pin_sol)
+        barrier()
+        dist.destroy_process_group()
+        return 0
+    if not a.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         ms, n_s, it = cpu_reference_run(pkg, a.mesh, a.cpu_h, 1, 1, threads)
         line["cpu_baseline"] = {
@@ -330,6 +371,9 @@ def main():
     L.nsb_free_pinned(pin_bc)
     L.nsb_free_pinned(pin_sol)
     print(json.dumps(line))
+    if dist is not None:
+        barrier()
+        dist.destroy_process_group()
     return 0
 
 

@@ -66,6 +66,8 @@ struct nsb_ctx {
   int kF = 3, kS = 20;           // values in effect for the current step
   double rF = 6.0, rS = 300.0;
   DevBuf<double> mdiag;          // diagonal of the velocity mass matrix (owned nodes)
+  DevBuf<double> upad, zpadA, zpadB;  // padded [node][PAD] gather sources of the F kernels
+  int pad = 4, fs_L = 0;
   // Krylov work space
   DevBuf<double> V, tmpN, hdev, partials, coef;
   DevBuf<unsigned> counter;
@@ -193,9 +195,9 @@ void allreduce_sum(nsb_ctx *c, double *buf, size_t count) {
 
 // Refresh the velocity ghosts of x from their owners (Epetra Import of the
 // reference's vmult; `solution = solution_owned`, reference :395).
-void halo_exchange(nsb_ctx *c, double *x) {
+void halo_exchange(nsb_ctx *c, double *x, int width = 0 /* doubles per node: dim (default) or the pad */) {
   if (c->nranks == 1 || c->neighbors.empty()) return;
-  const int d = c->dim;
+  const int d = width > 0 ? width : c->dim;
   const int64_t ns = c->send_ptr.back();
   if (ns > 0)
     NSB_LAUNCH(c, halo_pack_kernel, blocks_for(ns * d), 256, ns, d, c->send_idx.p, x, c->send_buf.p);
@@ -204,7 +206,8 @@ void halo_exchange(nsb_ctx *c, double *x) {
     const int64_t sb = c->send_ptr[k], sn = c->send_ptr[k + 1] - sb, rb = c->recv_ptr[k], rn = c->recv_ptr[k + 1] - rb;
     if (sn > 0) NSB_NCCL(nccl().Send(c->send_buf.p + sb * d, (size_t)sn * d, ncclDouble, c->neighbors[k], c->comm, c->stream));
     if (rn > 0)
-      NSB_NCCL(nccl().Recv(x + (int64_t)c->n_u + rb * d, (size_t)rn * d, ncclDouble, c->neighbors[k], c->comm, c->stream));
+      NSB_NCCL(nccl().Recv(x + (int64_t)c->n_own_nodes * d + rb * d, (size_t)rn * d, ncclDouble, c->neighbors[k], c->comm,
+                           c->stream));
   }
   NSB_NCCL(nccl().GroupEnd());
 }
@@ -269,14 +272,24 @@ void cheb_sweep(nsb_ctx *c, const CsrDev &M, const double *dinv, const double *b
   if (L == 32) NSB_LAUNCH(c, cheb_sweep_kernel<32>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
 }
 
-int pick_L_nodes(const CsrDev &F) {
+int pick_L_nodes(const CsrDev &F) {  // measured on B200: 4 lanes per ~28-entry node row beat 8 and 16
   const double mean = F.n_rows ? (double)F.nnz / (double)F.n_rows : 0.0;
-  return mean < 12 ? 4 : mean < 48 ? 8 : 16;
+  return mean < 48 ? 4 : mean < 96 ? 8 : 16;
 }
 
 // y_u = F x_u (+ A01 x_p)  [mode 0]  or  y = d .* (F x_u)  [mode 3]
-void fs_apply(nsb_ctx *c, int mode, bool with_a01, const double *xu, const double *xp, const double *d, double *y) {
-  const int L = pick_L_nodes(c->fs);
+void pad_nodes(nsb_ctx *c, const double *x, double *xpad) {
+  const int64_t nn = c->n_uloc / c->dim;
+  if (c->dim == 2)
+    NSB_LAUNCH(c, pad_nodes_kernel<2>, blocks_for(nn * c->pad), 256, nn, x, xpad);
+  else
+    NSB_LAUNCH(c, pad_nodes_kernel<3>, blocks_for(nn * c->pad), 256, nn, x, xpad);
+}
+
+void fs_apply(nsb_ctx *c, int mode, bool with_a01, const double *xu_std, const double *xp, const double *d, double *y) {
+  pad_nodes(c, xu_std, c->upad.p);
+  const double *xu = c->upad.p;
+  const int L = c->fs_L ? c->fs_L : pick_L_nodes(c->fs);
   const unsigned grid = blocks_for(c->fs.n_rows * L);
   CsrView a01 = c->a01.view();
   if (!with_a01) a01.rowptr = nullptr;
@@ -293,12 +306,17 @@ void fs_apply(nsb_ctx *c, int mode, bool with_a01, const double *xu, const doubl
 #undef NSB_FS_CASE
 }
 
-void fs_cheb_sweep(nsb_ctx *c, const double *dinv, const double *b, const double *z, double *d, double *znew,
-                   double c1, double c2) {
-  const int L = pick_L_nodes(c->fs);
+void fs_cheb_sweep(nsb_ctx *c, const double *dinv, const double *b, const double *zpad, double *d, double *znew,
+                   bool out_std, double c1, double c2) {
+  const int L = c->fs_L ? c->fs_L : pick_L_nodes(c->fs);
   const unsigned grid = blocks_for(c->fs.n_rows * L);
-#define NSB_FC_CASE(DD, LL) \
-  if (c->dim == DD && L == LL) NSB_LAUNCH(c, (fs_cheb_sweep_kernel<DD, LL>), grid, 256, c->fs.view(), dinv, b, z, d, znew, c1, c2)
+#define NSB_FC_CASE(DD, LL)                                                                                          \
+  if (c->dim == DD && L == LL) {                                                                                     \
+    if (out_std)                                                                                                     \
+      NSB_LAUNCH(c, (fs_cheb_sweep_kernel<DD, LL, true>), grid, 256, c->fs.view(), dinv, b, zpad, d, znew, c1, c2);  \
+    else                                                                                                             \
+      NSB_LAUNCH(c, (fs_cheb_sweep_kernel<DD, LL, false>), grid, 256, c->fs.view(), dinv, b, zpad, d, znew, c1, c2); \
+  }
   NSB_FC_CASE(2, 4);
   NSB_FC_CASE(2, 8);
   NSB_FC_CASE(2, 16);
@@ -308,23 +326,44 @@ void fs_cheb_sweep(nsb_ctx *c, const double *dinv, const double *b, const double
 #undef NSB_FC_CASE
 }
 
+// vec ~= F^{-1} b: degree-k Chebyshev-Jacobi polynomial on the node-block F, zero initial guess.
+// The iterate lives in padded buffers (gather source); the last sweep writes `out` in standard layout.
+void cheb_solve_F(nsb_ctx *c, const double *b, double *out, double *d, int k, double lmax, double ratio) {
+  const int64_t n = c->n_u;
+  const double *dinv = c->di.p;
+  const double lmin = lmax / ratio, theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  if (k <= 1) {
+    NSB_LAUNCH(c, cheb_first_kernel, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, out);
+    return;
+  }
+  double *z = c->zpadA.p, *zn = c->zpadB.p;
+  if (c->dim == 2)
+    NSB_LAUNCH(c, fs_cheb_first_kernel<2>, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, z);
+  else
+    NSB_LAUNCH(c, fs_cheb_first_kernel<3>, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, z);
+  double rho = 1.0 / sigma;
+  for (int i = 1; i < k; ++i) {
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    const bool last = i == k - 1;
+    halo_exchange(c, z, c->pad);
+    fs_cheb_sweep(c, dinv, b, z, d, last ? out : zn, last, rho_new * rho, 2.0 * rho_new / delta);
+    std::swap(z, zn);
+    rho = rho_new;
+  }
+}
+
 // out ~= M^{-1} b by a degree-k Chebyshev-Jacobi polynomial (zero initial
 // guess) targeting the interval [lmax/ratio, lmax] of D^{-1} M.
-void cheb_solve(nsb_ctx *c, const CsrDev *M /* nullptr: the velocity block F */, const double *dinv, const double *b,
-                double *out, double *scratch, double *d, int k, double lmax, double ratio) {
-  const int64_t n = M ? M->n_rows : (int64_t)c->n_u;
+void cheb_solve(nsb_ctx *c, const CsrDev *M, const double *dinv, const double *b, double *out, double *scratch,
+                double *d, int k, double lmax, double ratio) {
+  const int64_t n = M->n_rows;
   const double lmin = lmax / ratio, theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   double *z = ((k - 1) % 2 == 0) ? out : scratch, *zn = ((k - 1) % 2 == 0) ? scratch : out;
   NSB_LAUNCH(c, cheb_first_kernel, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, z);
   double rho = 1.0 / sigma;
   for (int i = 1; i < k; ++i) {
     const double rho_new = 1.0 / (2.0 * sigma - rho);
-    if (M)
-      cheb_sweep(c, *M, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta);
-    else {
-      halo_exchange(c, z);
-      fs_cheb_sweep(c, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta);
-    }
+    cheb_sweep(c, *M, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta);
     std::swap(z, zn);
     rho = rho_new;
   }
@@ -530,6 +569,19 @@ void finalize_setup(nsb_ctx *c) {
   dz(c->eig_w, std::max<int64_t>(c->n_uloc, c->n_p));
   dz(c->force_out, 2);
   dz(c->mdiag, (size_t)c->n_own_nodes);
+  c->pad = c->dim == 3 ? 4 : 2;
+  {
+    const size_t np_ = (size_t)(c->n_uloc / c->dim) * c->pad;
+    dz(c->upad, np_);
+    dz(c->zpadA, np_);
+    dz(c->zpadB, np_);
+    if (c->send_ptr.size() > 1 && c->send_ptr.back() > 0)
+      c->send_buf.alloc((size_t)c->send_ptr.back() * std::max(c->dim, c->pad), &c->dev_bytes);
+  }
+  if (const char *e = std::getenv("NSB_FS_L")) {
+    const int L = std::atoi(e);
+    if (L == 4 || L == 8 || L == 16) c->fs_L = L;
+  }
   if (c->dim == 2)
     NSB_LAUNCH(c, mass_diag_kernel<2>, blocks_for(c->n_cells), 256, c->n_cells, c->xyz.p, c->cell_verts.p,
                c->cell_nodes.p, c->n_own_nodes, c->fe.p, c->mdiag.p);
@@ -784,7 +836,7 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
     return;
   }
   // vec0 ~= F^-1 src0                                   (:978-981)
-  cheb_solve(c, nullptr, c->di.p, src, c->vec0.p, c->chz_u.p, c->chd_u.p, c->kF, c->lamF, c->rF);
+  cheb_solve_F(c, src, c->vec0.p, c->chd_u.p, c->kF, c->lamF, c->rF);
   // vec1 = src1 - B vec0                                 (:982-983)
   halo_exchange(c, c->vec0.p);
   spmv(c, c->a10, 1, c->vec0.p, src + c->n_uloc + c->p_begin, nullptr, c->vec1.p + c->p_begin);
@@ -1368,7 +1420,7 @@ int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
           NSB_LAUNCH(c, schur_outer_kernel, blocks_for((int64_t)c->n_u * 32), 256, c->a01.view(), c->a10t.p, c->di.p,
                      c->s.view());
           break;
-        case 4: fs_cheb_sweep(c, c->di.p, c->rhs.p, c->vec0.p, c->chd_u.p, c->chz_u.p, 0.5, 0.5); break;
+        case 4: fs_cheb_sweep(c, c->di.p, c->rhs.p, c->zpadA.p, c->chd_u.p, c->zpadB.p, false, 0.5, 0.5); break;
         case 6: cheb_sweep(c, c->s, c->dis.p, c->vec1.p, c->chz_p.p, c->chd_p.p, c->chz_p2.p, 0.5, 0.5); break;
         default: throw ArgError("nsb_bench_kernel: unknown kernel id");
       }
