@@ -331,8 +331,14 @@ def main():
               "fs_apply_kernel + spmv_kernel (block product y = A x)": (ms_spmv, spmv_gbs, spmv_bytes(info, dim),
                                                                        ms_spmv)}
     top = max(shares, key=lambda k: shares[k][0])
+    traffic = None
+    try:  # measured DRAM bytes per launch of that kernel at this mesh size, when a capture exists (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic = tj.get(top.split(" ")[0], {}).get(str(a.h)) if world == 1 else None
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": top, "achieved": shares[top][1], "peak": hbm_peak, "unit": "GB/s",
-            "frac": shares[top][1] / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "frac": shares[top][1] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
             "ms_per_launch": shares[top][3], "algorithmic_bytes_per_launch": shares[top][2],
             "ms_per_gmres_iteration_by_kernel": {k: v[0] for k, v in shares.items()}}
     line = {"metric": "time_per_step", "value": ms_dev, "unit": "ms/step", "n_gpus": a.gpus, "steps": a.steps,

@@ -166,6 +166,10 @@ int nsb_set_local_dofs(nsb_ctx *ctx, int rank, int n_ranks, uint32_t n_own_nodes
  * and receive into the ghost slots [recv_ptr[k], recv_ptr[k+1]). */
 int nsb_set_halo(nsb_ctx *ctx, int n_neighbors, const int32_t *neighbors, const int64_t *send_ptr,
                  const uint32_t *send_idx, const int64_t *recv_ptr);
+/* Collects the owned velocity dofs of all ranks into one vector in the distributed numbering
+ * (node_offsets: n_ranks+1 owned-node offsets; out_host: dim * node_offsets[n_ranks] doubles, same
+ * content on every rank).  The pressure part of nsb_get_solution is already replicated. */
+int nsb_gather_velocity(nsb_ctx *ctx, const uint32_t *node_offsets, double *out_host);
 
 #ifdef __cplusplus
 }

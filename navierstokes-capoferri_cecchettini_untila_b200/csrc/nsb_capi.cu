@@ -1470,6 +1470,27 @@ void nsb_free_pinned(void *p) {
   if (p) cudaFreeHost(p);
 }
 
+int nsb_gather_velocity(nsb_ctx *c, const uint32_t *node_offsets, double *out_host) {
+  return guarded(c, [&] {
+    if (!c->sol.p || !node_offsets || !out_host) throw ArgError("nsb_gather_velocity: null input / no solution");
+    const int d = c->dim;
+    const size_t total = (size_t)d * node_offsets[c->nranks];
+    DevBuf<double> g;
+    g.alloc(total);
+    NSB_CUDA(cudaMemcpyAsync(g.p + (size_t)d * node_offsets[c->rank], c->sol.p, (size_t)c->n_u * sizeof(double),
+                             cudaMemcpyDeviceToDevice, c->stream));
+    if (c->nranks > 1) {
+      NSB_NCCL(nccl().GroupStart());
+      for (int r = 0; r < c->nranks; ++r) {
+        const size_t off = (size_t)d * node_offsets[r], cnt = (size_t)d * (node_offsets[r + 1] - node_offsets[r]);
+        if (cnt) NSB_NCCL(nccl().Broadcast(g.p + off, g.p + off, cnt, ncclDouble, r, c->comm, c->stream));
+      }
+      NSB_NCCL(nccl().GroupEnd());
+    }
+    g.download(out_host, c->stream);
+  });
+}
+
 int nsb_comm_unique_id(char id[128]) {
   try {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");

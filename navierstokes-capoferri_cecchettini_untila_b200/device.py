@@ -21,7 +21,7 @@ SYMBOLS = [
     "nsb_set_dirichlet", "nsb_scale_dirichlet", "nsb_set_force_faces", "nsb_assemble", "nsb_solve_time_step",
     "nsb_compute_forces", "nsb_get_matrix_values", "nsb_get_pattern", "nsb_nnz", "nsb_get_rhs", "nsb_vmult",
     "nsb_bench_kernel", "nsb_launch_count", "nsb_timers", "nsb_info", "nsb_alloc_pinned", "nsb_free_pinned",
-    "nsb_comm_unique_id", "nsb_comm_init", "nsb_set_local_dofs", "nsb_set_halo", "nsb_set_schur_solver",
+    "nsb_comm_unique_id", "nsb_comm_init", "nsb_set_local_dofs", "nsb_set_halo", "nsb_set_schur_solver", "nsb_gather_velocity",
 ]
 
 
@@ -80,6 +80,7 @@ def device_lib():
         i32p = C.POINTER(C.c_int32)
         L.nsb_set_local_dofs.argtypes = [p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p, u32p]
         L.nsb_set_halo.argtypes = [p, C.c_int, i32p, i64p, u32p, i64p]
+        L.nsb_gather_velocity.argtypes = [p, u32p, f64p]
         _lib = L
     return _lib
 
@@ -197,6 +198,13 @@ class Device:
 
     def set_inner(self, sweeps_F, eig_ratio_F, sweeps_S, eig_ratio_S):
         self._chk(self.L.nsb_set_inner(self.h, sweeps_F, eig_ratio_F, sweeps_S, eig_ratio_S))
+
+    def gather_velocity(self, node_offsets):
+        """All ranks' owned velocity dofs in the distributed numbering (collective)."""
+        no = np.ascontiguousarray(node_offsets, np.uint32)
+        out = np.empty(self.dim * int(no[-1]), np.float64)
+        self._chk(self.L.nsb_gather_velocity(self.h, _p(no, C.c_uint32), _p(out, C.c_double)))
+        return out
 
     def set_schur_solver(self, mode=1, smoother_sweeps=0, theta=0.0, omega=0.0, cycles=0):
         self._chk(self.L.nsb_set_schur_solver(self.h, mode, smoother_sweeps, theta, omega, cycles))

@@ -8,7 +8,13 @@
 #include <cstdlib>
 #include <iomanip>
 
+#include <unistd.h>
+
+#include <cstdio>
+#include <thread>
+
 #include "../../include/nsb.h"
+#include "distribute.hpp"
 #include "problem.hpp"
 
 namespace {
@@ -82,6 +88,15 @@ void NavierStokes::setup() {
   const int device = (int)env_uint("LOCAL_RANK", 0);
   if (nsb_create(dim, device, &ctx) != NSB_OK)
     throw std::runtime_error("NavierStokes::setup: no usable CUDA device (there is no CPU path)");
+  if (mpi_size > 1) {
+    setup_distributed();
+    if (pcout) {
+      std::cout << "\tInitializing the system right-hand side" << std::endl;
+      std::cout << "\tInitializing the solution vector" << std::endl;
+    }
+    solution.assign((size_t)d.n_u + d.n_p, 0.0);
+    return;
+  }
   const nsb::Mesh &m = problem->mesh;
   const nsb::Patterns &P = problem->pat;
   check(nsb_set_mesh(ctx, (int64_t)m.n_verts(), m.xyz.data(), (int64_t)m.n_cells(), m.cells.data()), "nsb_set_mesh");
@@ -130,9 +145,115 @@ void NavierStokes::refresh_dirichlet(double t) {
     for (unsigned int r = 0; r < dim; ++r) p[r] = x[r];
     return inlet.value(p, (unsigned int)c);
   });
-  if (ctx)
+  if (!ctx) return;
+  if (mpi_size == 1) {
     check(nsb_set_dirichlet(ctx, (int64_t)problem->bc.dofs.size(), problem->bc.dofs.data(), problem->bc.values.data()),
           "nsb_set_dirichlet");
+    return;
+  }
+  if (!local) return;
+  // owned Dirichlet nodes of this rank, in local dof ids (the node set is fixed; only the values move)
+  const nsb::DofMap &d = problem->dofs;
+  std::vector<uint32_t> dofs;
+  std::vector<double> vals;
+  const uint32_t off = local->node_offset[mpi_rank], end = local->node_offset[mpi_rank + 1];
+  for (size_t i = 0; i + dim <= problem->bc.dofs.size(); i += dim) {
+    const uint32_t g = local->node_perm[problem->bc.dofs[i] / dim];
+    if (g < off || g >= end) continue;
+    for (unsigned int c = 0; c < dim; ++c) {
+      dofs.push_back(dim * (g - off) + c);
+      vals.push_back(problem->bc.values[i + c]);
+    }
+  }
+  (void)d;
+  check(nsb_set_dirichlet(ctx, (int64_t)dofs.size(), dofs.data(), vals.data()), "nsb_set_dirichlet");
+}
+
+// One process per GPU: RANK / WORLD_SIZE / LOCAL_RANK from the launcher (torchrun-style).  The NCCL id is
+// handed from rank 0 to the others through a file named after the common parent process.
+void NavierStokes::setup_distributed() {
+  problem->has_boundary = true;  // bfaces / ff / bc were built in setup()
+  problem->partition((int)mpi_size);
+  local = std::make_unique<nsb::LocalProblem>(nsb::localize(*problem, (int)mpi_size, (int)mpi_rank));
+  const nsb::LocalProblem &L = *local;
+  const nsb::Mesh &m = problem->mesh;
+  check(nsb_set_mesh(ctx, (int64_t)m.n_verts(), m.xyz.data(), (int64_t)L.cells.size(), L.cell_verts.data()), "nsb_set_mesh");
+  check(nsb_set_local_dofs(ctx, (int)mpi_rank, (int)mpi_size, L.n_own, L.n_ghost, L.n_p, L.p_offset.data(),
+                           L.cell_nodes.data(), L.cell_pverts.data()),
+        "nsb_set_local_dofs");
+  check(nsb_set_halo(ctx, (int)L.neighbors.size(), L.neighbors.data(), L.send_ptr.data(), L.send_idx.data(),
+                     L.recv_ptr.data()),
+        "nsb_set_halo");
+  char id[128];
+  const char *rdv = std::getenv("NSB_RENDEZVOUS");
+  const std::string path = rdv ? rdv : "/tmp/nsb_nccl_id_" + std::to_string((long)getppid());
+  if (mpi_rank == 0) {
+    if (nsb_comm_unique_id(id) != NSB_OK) throw std::runtime_error("nsb_comm_unique_id failed (libnccl.so.2?)");
+    const std::string tmp = path + ".tmp";
+    FILE *f = std::fopen(tmp.c_str(), "wb");
+    if (!f || std::fwrite(id, 1, 128, f) != 128) throw std::runtime_error("cannot write " + tmp);
+    std::fclose(f);
+    std::rename(tmp.c_str(), path.c_str());
+  } else {
+    bool got = false;
+    for (int tries = 0; tries < 1200 && !got; ++tries) {
+      if (FILE *f = std::fopen(path.c_str(), "rb")) {
+        got = std::fread(id, 1, 128, f) == 128;
+        std::fclose(f);
+      }
+      if (!got) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+    }
+    if (!got) throw std::runtime_error("timed out waiting for the NCCL id at " + path);
+  }
+  check(nsb_comm_init(ctx, (int)mpi_rank, (int)mpi_size, id), "nsb_comm_init");
+  if (mpi_rank == 0) std::remove(path.c_str());  // every rank has joined once comm_init returns
+  check(nsb_set_node_pattern(ctx, L.fs.n_rows, L.fs.rowptr.data(), L.fs.colind.data()), "nsb_set_node_pattern");
+  check(nsb_set_pattern(ctx, NSB_A01, L.a01.n_rows, L.a01.rowptr.data(), L.a01.colind.data()), "nsb_set_pattern(A01)");
+  check(nsb_set_pattern(ctx, NSB_A10, L.a10.n_rows, L.a10.rowptr.data(), L.a10.colind.data()), "nsb_set_pattern(A10)");
+  check(nsb_set_pattern(ctx, NSB_S, L.s.n_rows, L.s.rowptr.data(), L.s.colind.data()), "nsb_set_pattern(S)");
+  check(nsb_set_quadrature(ctx, quad_rule), "nsb_set_quadrature");
+  check(nsb_set_force_faces(ctx, (int64_t)L.ff_cell.size(), L.ff_cell.data(), L.ff_normal.data(), L.ff_measure.data()),
+        "nsb_set_force_faces");
+  check(nsb_set_params(ctx, deltat, nu), "nsb_set_params");
+  check(nsb_set_solver(ctx, opt_rtol, opt_restart, opt_max_it, 0.5, NSB_PREC_ASIMPLE), "nsb_set_solver");
+  refresh_dirichlet(0.0);
+  check(nsb_finalize_setup(ctx), "nsb_finalize_setup");
+  local_vec.assign((size_t)dim * (L.n_own + L.n_ghost) + L.n_p, 0.0);
+}
+
+void NavierStokes::push_solution() {
+  if (mpi_size == 1) {
+    check(nsb_set_solution(ctx, solution.data()), "nsb_set_solution");
+    return;
+  }
+  const nsb::LocalProblem &L = *local;
+  const nsb::DofMap &d = problem->dofs;
+  std::vector<uint32_t> canon(d.n_nodes);  // distributed id -> canonical node
+  for (uint32_t A = 0; A < d.n_nodes; ++A) canon[L.node_perm[A]] = A;
+  const uint32_t off = L.node_offset[mpi_rank];
+  for (uint32_t i = 0; i < L.n_own + L.n_ghost; ++i) {
+    const uint32_t A = canon[i < L.n_own ? off + i : L.ghost_dist[i - L.n_own]];
+    for (unsigned int c = 0; c < dim; ++c) local_vec[(size_t)dim * i + c] = solution[(size_t)dim * A + c];
+  }
+  const size_t pu = (size_t)dim * (L.n_own + L.n_ghost);
+  for (uint32_t V = 0; V < d.n_p; ++V) local_vec[pu + L.p_perm[V]] = solution[(size_t)d.n_u + V];
+  check(nsb_set_solution(ctx, local_vec.data()), "nsb_set_solution");
+}
+
+void NavierStokes::pull_solution() {
+  if (mpi_size == 1) {
+    check(nsb_get_solution(ctx, solution.data()), "nsb_get_solution");
+    return;
+  }
+  const nsb::LocalProblem &L = *local;
+  const nsb::DofMap &d = problem->dofs;
+  std::vector<double> g((size_t)d.n_u);
+  check(nsb_gather_velocity(ctx, L.node_offset.data(), g.data()), "nsb_gather_velocity");
+  check(nsb_get_solution(ctx, local_vec.data()), "nsb_get_solution");
+  for (uint32_t A = 0; A < d.n_nodes; ++A)
+    for (unsigned int c = 0; c < dim; ++c) solution[(size_t)dim * A + c] = g[(size_t)dim * L.node_perm[A] + c];
+  const size_t pu = (size_t)dim * (L.n_own + L.n_ghost);
+  for (uint32_t V = 0; V < d.n_p; ++V) solution[(size_t)d.n_u + V] = local_vec[pu + L.p_perm[V]];
 }
 
 // reference :133-330
@@ -168,7 +289,7 @@ void NavierStokes::solve_time_step(std::ostream &oss) {
     std::cout << std::endl;
   }
   oss << iters << "," << t_prec << "," << t_sol << ",";
-  check(nsb_get_solution(ctx, solution.data()), "nsb_get_solution");  // solution = solution_owned (:395)
+  pull_solution();  // solution = solution_owned (:395)
 }
 
 // reference :831-929
@@ -201,7 +322,7 @@ void NavierStokes::solve(unsigned int time_step) {
     if (pcout) std::cout << "Continuing execution from time step " << time_step << std::endl;
     import_data(time_step);
   }
-  check(nsb_set_solution(ctx, solution.data()), "nsb_set_solution");
+  push_solution();
   export_data(time_step);
   if (pcout) std::cout << "---------------------------------------------------" << std::endl;
   while (time < T - 0.5 * deltat) {
@@ -257,7 +378,7 @@ void NavierStokes::import_data(const unsigned int &time_step) {
   f.read(reinterpret_cast<char *>(inbuff.data()), (std::streamsize)(inbuff.size() * sizeof(double)));
   if (!f) throw std::runtime_error("import_data: cannot read " + file_name);
   for (size_t i = 0; i < solution.size(); ++i) solution[i] = inbuff[renumbered_dofs[i]];
-  if (ctx) check(nsb_set_solution(ctx, solution.data()), "nsb_set_solution");
+  if (ctx) push_solution();
 }
 
 // reference :808-828
@@ -281,7 +402,11 @@ void NavierStokes::output(const unsigned int &time_step) const {
   const nsb::Mesh &m = problem->mesh;
   const nsb::DofMap &d = problem->dofs;
   const int nv = dim + 1, NN = d.nn();
-  const size_t nc = m.n_cells();
+  // each rank writes the cells its partition owns (one piece per rank, like write_vtu_with_pvtu_record)
+  std::vector<size_t> mine;
+  for (size_t c = 0; c < m.n_cells(); ++c)
+    if (mpi_size == 1 || problem->part_cell[c] == (int)mpi_rank) mine.push_back(c);
+  const size_t nc = mine.size();
   const std::string base = "output-stokes_" + std::to_string(time_step);
   const std::string piece = base + "." + std::to_string(mpi_rank) + ".vtu";
   std::ofstream f("../output/" + piece);
@@ -290,8 +415,9 @@ void NavierStokes::output(const unsigned int &time_step) const {
   f << "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n"
     << "<UnstructuredGrid>\n<Piece NumberOfPoints=\"" << nc * nv << "\" NumberOfCells=\"" << nc << "\">\n";
   f << "<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
-  for (size_t c = 0; c < nc; ++c)
+  for (size_t ci = 0; ci < nc; ++ci)
     for (int a = 0; a < nv; ++a) {
+      const size_t c = mine[ci];
       const double *p = &m.xyz[(size_t)m.cells[c * nv + a] * dim];
       f << p[0] << " " << p[1] << " " << (dim == 3 ? p[2] : 0.0) << "\n";
     }
@@ -303,17 +429,17 @@ void NavierStokes::output(const unsigned int &time_step) const {
   for (size_t c = 0; c < nc; ++c) f << (dim == 2 ? 5 : 10) << "\n";
   f << "</DataArray>\n</Cells>\n<PointData Scalars=\"scalars\">\n";
   f << "<DataArray type=\"Float64\" Name=\"velocity\" NumberOfComponents=\"3\" format=\"ascii\">\n";
-  for (size_t c = 0; c < nc; ++c)
+  for (size_t ci = 0; ci < nc; ++ci)
     for (int a = 0; a < nv; ++a) {
-      const size_t node = d.cell_nodes[c * NN + a];
+      const size_t node = d.cell_nodes[mine[ci] * NN + a];
       for (int k = 0; k < 3; ++k) f << (k < (int)dim ? solution[dim * node + k] : 0.0) << (k == 2 ? "\n" : " ");
     }
   f << "</DataArray>\n<DataArray type=\"Float64\" Name=\"pressure\" format=\"ascii\">\n";
-  for (size_t c = 0; c < nc; ++c)
-    for (int a = 0; a < nv; ++a) f << solution[(size_t)d.n_u + d.cell_pverts[c * nv + a]] << "\n";
+  for (size_t ci = 0; ci < nc; ++ci)
+    for (int a = 0; a < nv; ++a) f << solution[(size_t)d.n_u + d.cell_pverts[mine[ci] * nv + a]] << "\n";
   f << "</DataArray>\n<DataArray type=\"Float64\" Name=\"partitioning\" format=\"ascii\">\n";
-  for (size_t c = 0; c < nc; ++c)
-    for (int a = 0; a < nv; ++a) f << (problem->part_cell.empty() ? 0 : problem->part_cell[c]) << "\n";
+  for (size_t ci = 0; ci < nc; ++ci)
+    for (int a = 0; a < nv; ++a) f << (problem->part_cell.empty() ? 0 : problem->part_cell[mine[ci]]) << "\n";
   f << "</DataArray>\n</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n";
   if (mpi_rank == 0) {
     std::ofstream pv("../output/" + base + ".pvtu");

@@ -85,6 +85,7 @@ struct MPI_InitFinalize {
 struct nsb_ctx;
 namespace nsb {
 struct Problem;
+struct LocalProblem;
 }
 
 class NavierStokes {
@@ -161,6 +162,8 @@ protected:
   const unsigned int degree_velocity, degree_pressure;
 
   std::unique_ptr<nsb::Problem> problem;  // mesh, dof numbering, patterns (host)
+  std::unique_ptr<nsb::LocalProblem> local;  // this rank's part when mpi_size > 1 (one process per GPU)
+  std::vector<double> local_vec;             // [u owned | u ghost | p] staging for the distributed context
   nsb_ctx *ctx = nullptr;                 // device-resident system (system_matrix, system_rhs, solution_owned)
   std::vector<double> solution;           // host mirror of the ghosted solution (reference NavierStokes.hpp:252)
   std::vector<unsigned int> renumbered_dofs;
@@ -186,6 +189,9 @@ protected:
 
   void check(int rc, const char *what) const;
   void refresh_dirichlet(double time);
+  void setup_distributed();
+  void push_solution();  // host `solution` (canonical numbering) -> device
+  void pull_solution();  // device -> host `solution` (collective when mpi_size > 1)
 };
 
 #endif
