@@ -68,6 +68,13 @@ struct nsb_ctx {
   DevBuf<double> mdiag;          // diagonal of the velocity mass matrix (owned nodes)
   DevBuf<double> upad, zpadA, zpadB;  // padded [node][PAD] gather sources of the F kernels
   int pad = 4, fs_L = 0;
+  // The preconditioner application is a fixed sequence of ~100 short launches per outer iteration: it is
+  // captured into a CUDA graph once per time step (tmpN -> pz) and replayed (NSB_GRAPH=0 disables).
+  DevBuf<double> pz;
+  cudaGraph_t prec_graph = nullptr;
+  cudaGraphExec_t prec_exec = nullptr;
+  int64_t prec_graph_kernels = 0;
+  bool use_graph = true, capturing = false;
   // Krylov work space
   DevBuf<double> V, tmpN, hdev, partials, coef;
   DevBuf<unsigned> counter;
@@ -136,7 +143,10 @@ inline unsigned blocks_for(int64_t n_threads, int block = 256) { return (unsigne
 #define NSB_LAUNCH(c, kernel, grid, block, ...)                  \
   do {                                                           \
     kernel<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);    \
-    ++(c)->launches;                                             \
+    if ((c)->capturing)                                          \
+      ++(c)->prec_graph_kernels;                                 \
+    else                                                         \
+      ++(c)->launches;                                           \
     NSB_CUDA(cudaGetLastError());                                \
   } while (0)
 
@@ -551,6 +561,8 @@ void finalize_setup(nsb_ctx *c) {
   dz(c->dis, c->n_p);
   dz(c->first_diag, 1);
   dz(c->tmpN, N);
+  dz(c->pz, N);
+  if (const char *e = std::getenv("NSB_GRAPH")) c->use_graph = std::atoi(e) != 0;
   dz(c->hdev, 2 * kMaxDots + 8);
   dz(c->partials, (size_t)kMaxDots * kRedBlocks);
   dz(c->coef, kMaxDots);
@@ -861,14 +873,70 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
   spmv(c, c->a01, 2, dst + c->n_uloc, c->vec0.p, c->di.p, dst);
 }
 
+// pz = P^-1 tmpN, as a CUDA graph captured once per time step (the coefficients of the sweeps change with
+// lambda_max and the polynomial degree, so the graph is re-captured and the executable updated in place).
+void prec_capture(nsb_ctx *c) {
+  const bool want = c->use_graph && c->prec == NSB_PREC_ASIMPLE && (c->nranks == 1 || std::getenv("NSB_GRAPH_NCCL"));
+  if (!want) {
+    if (c->prec_exec) cudaGraphExecDestroy(c->prec_exec);
+    c->prec_exec = nullptr;
+    return;
+  }
+  if (c->prec_graph) {
+    cudaGraphDestroy(c->prec_graph);
+    c->prec_graph = nullptr;
+  }
+  c->prec_graph_kernels = 0;
+  c->capturing = true;
+  cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+  if (e == cudaSuccess) {
+    try {
+      prec_apply(c, c->tmpN.p, c->pz.p);
+    } catch (...) {
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(c->stream, &g);
+      if (g) cudaGraphDestroy(g);
+      c->capturing = false;
+      throw;
+    }
+    e = cudaStreamEndCapture(c->stream, &c->prec_graph);
+  }
+  c->capturing = false;
+  if (e != cudaSuccess || !c->prec_graph) {
+    cudaGetLastError();
+    c->prec_graph = nullptr;
+    return;  // fall back to direct launches
+  }
+  if (c->prec_exec) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(c->prec_exec, c->prec_graph, &info) == cudaSuccess) return;
+    cudaGetLastError();
+    cudaGraphExecDestroy(c->prec_exec);
+    c->prec_exec = nullptr;
+  }
+  if (cudaGraphInstantiate(&c->prec_exec, c->prec_graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    c->prec_exec = nullptr;
+  }
+}
+
+void prec_apply_replay(nsb_ctx *c) {
+  if (c->prec_exec && c->prec_graph) {
+    NSB_CUDA(cudaGraphLaunch(c->prec_exec, c->stream));
+    c->launches += c->prec_graph_kernels;
+  } else
+    prec_apply(c, c->tmpN.p, c->pz.p);
+}
+
 // ---- GMRES, reference :348-350, 377 ---------------------------
 int gmres_solve(nsb_ctx *c, double tol) {
   ensure_krylov(c);
   const int64_t N = c->N;
   const int m = c->restart;
   std::vector<double> H((size_t)(m + 1) * m, 0.0), gamma(m + 1), ci(m), si(m), h(m + 2), h2(m + 2), y(m);
-  double *x = c->sol.p, *b = c->rhs.p, *p = c->tmpN.p, *V = c->V.p;
+  double *x = c->sol.p, *b = c->rhs.p, *p = c->tmpN.p, *V = c->V.p, *pz = c->pz.p;
   double *hd = c->hdev.p;
+  prec_capture(c);
   int its = 0;
   bool iterate = true, failed = false;
   auto check = [&](double res) {
@@ -884,18 +952,18 @@ int gmres_solve(nsb_ctx *c, double tol) {
     // v0 = P^-1 (b - A x)
     block_spmv(c, x, p);
     NSB_LAUNCH(c, axpby_kernel, kRedBlocks, 256, N, 1.0, b, -1.0, p);
-    prec_apply(c, p, V);
-    double rho = norm2_host(c, V, Part::FULL);
+    prec_apply_replay(c);  // pz = P^-1 p
+    double rho = norm2_host(c, pz, Part::FULL);
     iterate = check(rho);
     if (!iterate) break;
     gamma[0] = rho;
-    NSB_LAUNCH(c, scale_kernel, kRedBlocks, 256, N, 1.0 / rho, V, V);
+    NSB_LAUNCH(c, scale_kernel, kRedBlocks, 256, N, 1.0 / rho, pz, V);
     int dim = 0;
     for (int j = 0; j < m && iterate; ++j) {
       ++its;
-      double *vv = V + (size_t)(j + 1) * N;
+      double *vv = pz;  // orthogonalised in place, then scaled into V_{j+1}
       block_spmv(c, V + (size_t)j * N, p);
-      prec_apply(c, p, vv);
+      prec_apply_replay(c);
       dim = j + 1;
       // CGS2: h = V^T vv; vv -= V h; h2 = V^T vv; vv -= V h2; s = ||vv||
       multi_dot(c, V, N, dim, vv, Part::FULL, false, hd);
@@ -910,7 +978,8 @@ int gmres_solve(nsb_ctx *c, double tol) {
       for (int i = 0; i < dim; ++i) h[i] += h2[i];
       const double s = std::sqrt(s2);
       h[j + 1] = s;
-      if (std::isfinite(1.0 / s)) NSB_LAUNCH(c, scale_kernel, kRedBlocks, 256, N, 1.0 / s, vv, vv);
+      NSB_LAUNCH(c, scale_kernel, kRedBlocks, 256, N, std::isfinite(1.0 / s) ? 1.0 / s : 1.0, vv,
+                 V + (size_t)(j + 1) * N);
       for (int i = 0; i < j; ++i) {
         const double d = h[i];
         h[i] = ci[i] * d + si[i] * h[i + 1];
@@ -997,6 +1066,8 @@ void nsb_destroy(nsb_ctx *c) {
   }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->prec_exec) cudaGraphExecDestroy(c->prec_exec);
+  if (c->prec_graph) cudaGraphDestroy(c->prec_graph);
   cudaStream_t s = c->stream;
   delete c;
   if (s) cudaStreamDestroy(s);
