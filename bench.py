@@ -365,6 +365,7 @@ def main():
         L.nsb_free_pinned(pin_bc)
         L.nsb_free_pinned(pin_sol)
         barrier()
+        dev.close()
         dist.destroy_process_group()
         return 0
     if not a.no_cpu_baseline and world == 1:
@@ -376,9 +377,10 @@ def main():
                        f"scaled linearly in DoFs to {N}; assembly on {threads} threads, solve serial")}
     L.nsb_free_pinned(pin_bc)
     L.nsb_free_pinned(pin_sol)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if dist is not None:
         barrier()
+        dev.close()
         dist.destroy_process_group()
     return 0
 

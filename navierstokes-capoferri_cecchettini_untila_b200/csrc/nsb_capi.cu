@@ -75,6 +75,9 @@ struct nsb_ctx {
   cudaGraphExec_t prec_exec = nullptr;
   int64_t prec_graph_kernels = 0;
   bool use_graph = true, capturing = false;
+  // Optional L2 persistence window on the vector the F kernels gather from (NSB_L2_PERSIST=1).  Measured on
+  // B200 at 9.7 M DoFs: 0.677 ms per sweep with the window vs 0.625 ms without, so it is off by default.
+  size_t l2_persist_bytes = 0, l2_window_max = 0;
   // Krylov work space
   DevBuf<double> V, tmpN, hdev, partials, coef;
   DevBuf<unsigned> counter;
@@ -316,8 +319,25 @@ void fs_apply(nsb_ctx *c, int mode, bool with_a01, const double *xu_std, const d
 #undef NSB_FS_CASE
 }
 
+// mark `ptr` as the persisting L2 window for the next launches on the stream (nullptr: clear)
+void l2_window(nsb_ctx *c, const void *ptr, size_t bytes) {
+  if (!c->l2_persist_bytes) return;
+  cudaStreamAttrValue attr;
+  std::memset(&attr, 0, sizeof(attr));
+  if (ptr) {
+    const size_t win = std::min(bytes, c->l2_window_max);
+    attr.accessPolicyWindow.base_ptr = const_cast<void *>(ptr);
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_persist_bytes / (double)win);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  }
+  if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+}
+
 void fs_cheb_sweep(nsb_ctx *c, const double *dinv, const double *b, const double *zpad, double *d, double *znew,
                    bool out_std, double c1, double c2) {
+  l2_window(c, zpad, (size_t)(c->n_uloc / c->dim) * c->pad * sizeof(double));
   const int L = c->fs_L ? c->fs_L : pick_L_nodes(c->fs);
   const unsigned grid = blocks_for(c->fs.n_rows * L);
 #define NSB_FC_CASE(DD, LL)                                                                                          \
@@ -334,6 +354,7 @@ void fs_cheb_sweep(nsb_ctx *c, const double *dinv, const double *b, const double
   NSB_FC_CASE(3, 8);
   NSB_FC_CASE(3, 16);
 #undef NSB_FC_CASE
+  l2_window(c, nullptr, 0);
 }
 
 // vec ~= F^{-1} b: degree-k Chebyshev-Jacobi polynomial on the node-block F, zero initial guess.
@@ -563,6 +584,19 @@ void finalize_setup(nsb_ctx *c) {
   dz(c->tmpN, N);
   dz(c->pz, N);
   if (const char *e = std::getenv("NSB_GRAPH")) c->use_graph = std::atoi(e) != 0;
+  {
+    const char *e = std::getenv("NSB_L2_PERSIST");
+    cudaDeviceProp prop;
+    if ((e && std::atoi(e) != 0) && cudaGetDeviceProperties(&prop, c->device) == cudaSuccess &&
+        prop.persistingL2CacheMaxSize > 0) {
+      const size_t want = (size_t)prop.persistingL2CacheMaxSize;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        c->l2_persist_bytes = want;
+        c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+      } else
+        cudaGetLastError();
+    }
+  }
   dz(c->hdev, 2 * kMaxDots + 8);
   dz(c->partials, (size_t)kMaxDots * kRedBlocks);
   dz(c->coef, kMaxDots);
@@ -1058,6 +1092,11 @@ void nsb_destroy(nsb_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  // graphs that contain NCCL kernels must go before the communicator
+  if (c->prec_exec) cudaGraphExecDestroy(c->prec_exec);
+  if (c->prec_graph) cudaGraphDestroy(c->prec_graph);
+  c->prec_exec = nullptr;
+  c->prec_graph = nullptr;
   if (c->comm) {
     try {
       nccl().CommDestroy(c->comm);
@@ -1066,8 +1105,6 @@ void nsb_destroy(nsb_ctx *c) {
   }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
-  if (c->prec_exec) cudaGraphExecDestroy(c->prec_exec);
-  if (c->prec_graph) cudaGraphDestroy(c->prec_graph);
   cudaStream_t s = c->stream;
   delete c;
   if (s) cudaStreamDestroy(s);
