@@ -117,19 +117,26 @@ def spmv_canonical_bytes(info):
     return 12 * nnz + 8 * (2 * n_u + n_p + 3) + 16 * (n_u + n_p)
 
 
+def fs_slab_bytes(info, dim=3):
+    """F_s in slab storage (DESIGN.md §3-4): 10 B per stored non-zero (8 B value + 16-bit window index;
+    the ~3 % ELL padding is NOT counted), 4 B per window node, 4 B chunk-position word per row,
+    8 B slice offset per 32 virtual rows (~1.3 per row)."""
+    nnz = info["nnz_a00"] // (dim * dim)
+    n_nodes = info["n_u"] // dim
+    return 10 * nnz + 4 * info["slab_window_total"] + 4 * n_nodes + 8 * 8 * info["slab_count"]
+
+
 def spmv_bytes(info, dim=3):
-    """Same product on the storage the solver uses: A00 = F_s (x) I_dim kept as
-    the node-level scalar CSR F_s (nnz_a00 / dim^2 non-zeros)."""
+    """y = A x on the storage the solver uses: F_s in slab form, A01 / A10 as CSR;
+    x read once, y written once."""
     n_u, n_p = info["n_u"], info["n_p"]
-    nnz = info["nnz_a00"] // (dim * dim) + info["nnz_a01"] + info["nnz_a10"]
-    return 12 * nnz + 8 * (n_u // dim + n_u + n_p + 3) + 16 * (n_u + n_p)
+    return fs_slab_bytes(info, dim) + 12 * (info["nnz_a01"] + info["nnz_a10"]) + 8 * (n_u + n_p + 2) + 16 * (n_u + n_p)
 
 
 def sweep_bytes(info, dim=3):
-    """One Chebyshev-Jacobi sweep on F: F_s stream + z gathered once + b, dinv,
-    d, z_i read and d, znew written."""
-    n_u = info["n_u"]
-    return 12 * (info["nnz_a00"] // (dim * dim)) + 8 * (n_u // dim + 1) + 8 * n_u * 7
+    """One Chebyshev-Jacobi sweep on F: F_s stream + z read once (window staging; re-reads hit L2)
+    + b, dinv, d read and d, znew written."""
+    return fs_slab_bytes(info, dim) + 8 * info["n_u"] * 6
 
 
 def sweep_s_bytes(info):
@@ -324,11 +331,11 @@ def main():
     # share of one outer GMRES iteration: (kF-1) F sweeps, the fine-level S sweeps, one block product
     info2 = dev.info()
     kF_eff, kS_eff = info2["sweeps_F"], info2["sweeps_S"] + (1 if info2["schur_mode"] == 1 else 0)
-    shares = {"fs_cheb_sweep_kernel (Jacobi-type sweep on F, node-block CSR)": ((kF_eff - 1) * ms_sweep, sweep_gbs,
+    shares = {"fs_slab_sweep_kernel (Jacobi-type sweep on F, slab storage)": ((kF_eff - 1) * ms_sweep, sweep_gbs,
                                                                                sweep_bytes(info, dim), ms_sweep),
               "cheb_sweep_kernel (Jacobi-type sweep on S)": (max(kS_eff - 1, 1) * ms_sweep_s, sweep_s_gbs,
                                                              sweep_s_bytes(info), ms_sweep_s),
-              "fs_apply_kernel + spmv_kernel (block product y = A x)": (ms_spmv, spmv_gbs, spmv_bytes(info, dim),
+              "fs_slab_apply_kernel + spmv_kernel (block product y = A x)": (ms_spmv, spmv_gbs, spmv_bytes(info, dim),
                                                                        ms_spmv)}
     top = max(shares, key=lambda k: shares[k][0])
     traffic = None

@@ -135,8 +135,17 @@ int nsb_timers(const nsb_ctx *ctx, double out_ms[4]);
 /* info: [0] n_u [1] n_p [2] n_cells [3] nnz A00 (canonical) [4] nnz A01 [5] nnz A10 [6] nnz S
  *       [7] n_q [8] device bytes allocated [9] Chebyshev degree on F in effect
  *       [10] fine-level S sweeps per preconditioner application [11] Schur solver mode
- *       [12] number of levels of the Schur hierarchy */
-int nsb_info(const nsb_ctx *ctx, int64_t out[13]);
+ *       [12] number of levels of the Schur hierarchy
+ *       [13] entries of the slab storage of F_s incl. padding [14] sum of the slab windows (nodes)
+ *       [15] number of slabs */
+int nsb_info(const nsb_ctx *ctx, int64_t out[16]);
+
+/* Host-only check of the slab (windowed sliced-ELL) storage the solver kernels stream F_s from
+ * (csrc/slab.cuh): builds the layout from a node-level CSR pattern and evaluates y = (F_s (x) I_dim) x
+ * on the host in exactly the order the device kernels use.  No device is touched.
+ * stats: [0] slabs [1] stored entries [2] entries incl. padding [3] largest window [4] sum of windows. */
+int nsb_slab_host_check(int dim, int64_t n_rows, int64_t n_cols, const int64_t *rowptr, const uint32_t *colind,
+                        const double *val, uint32_t window_cap, const double *x, double *y, int64_t stats[5]);
 
 /* pinned host memory for callers that want asynchronous copies */
 void *nsb_alloc_pinned(int64_t bytes);

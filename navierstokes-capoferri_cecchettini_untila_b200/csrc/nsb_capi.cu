@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "forces.cuh"
 #include "krylov.cuh"
+#include "slab.cuh"
 #include "spmv.cuh"
 
 using namespace nsb;
@@ -66,8 +67,9 @@ struct nsb_ctx {
   int kF = 3, kS = 20;           // values in effect for the current step
   double rF = 6.0, rS = 300.0;
   DevBuf<double> mdiag;          // diagonal of the velocity mass matrix (owned nodes)
-  DevBuf<double> upad, zpadA, zpadB;  // padded [node][PAD] gather sources of the F kernels
-  int pad = 4, fs_L = 0;
+  SlabDev fslab;                 // F_s in slab (windowed sliced-ELL) form: what the solver kernels stream
+  size_t fslab_smem = 0;         // dynamic shared memory of the slab kernels
+  DevBuf<double> chzA, chzB;     // Chebyshev iterates on F (ping-pong)
   // The preconditioner application is a fixed sequence of ~100 short launches per outer iteration: it is
   // captured into a CUDA graph once per time step (tmpN -> pz) and replayed (NSB_GRAPH=0 disables).
   DevBuf<double> pz;
@@ -75,9 +77,6 @@ struct nsb_ctx {
   cudaGraphExec_t prec_exec = nullptr;
   int64_t prec_graph_kernels = 0;
   bool use_graph = true, capturing = false;
-  // Optional L2 persistence window on the vector the F kernels gather from (NSB_L2_PERSIST=1).  Measured on
-  // B200 at 9.7 M DoFs: 0.677 ms per sweep with the window vs 0.625 ms without, so it is off by default.
-  size_t l2_persist_bytes = 0, l2_window_max = 0;
   // Krylov work space
   DevBuf<double> V, tmpN, hdev, partials, coef;
   DevBuf<unsigned> counter;
@@ -143,9 +142,10 @@ int guarded(nsb_ctx *c, F &&f) {
 
 inline unsigned blocks_for(int64_t n_threads, int block = 256) { return (unsigned)((n_threads + block - 1) / block); }
 
-#define NSB_LAUNCH(c, kernel, grid, block, ...)                  \
+#define NSB_LAUNCH(c, kernel, grid, block, ...) NSB_LAUNCH_SMEM(c, kernel, grid, block, 0, __VA_ARGS__)
+#define NSB_LAUNCH_SMEM(c, kernel, grid, block, smem, ...)       \
   do {                                                           \
-    kernel<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);    \
+    kernel<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__); \
     if ((c)->capturing)                                          \
       ++(c)->prec_graph_kernels;                                 \
     else                                                         \
@@ -208,9 +208,9 @@ void allreduce_sum(nsb_ctx *c, double *buf, size_t count) {
 
 // Refresh the velocity ghosts of x from their owners (Epetra Import of the
 // reference's vmult; `solution = solution_owned`, reference :395).
-void halo_exchange(nsb_ctx *c, double *x, int width = 0 /* doubles per node: dim (default) or the pad */) {
+void halo_exchange(nsb_ctx *c, double *x) {
   if (c->nranks == 1 || c->neighbors.empty()) return;
-  const int d = width > 0 ? width : c->dim;
+  const int d = c->dim;
   const int64_t ns = c->send_ptr.back();
   if (ns > 0)
     NSB_LAUNCH(c, halo_pack_kernel, blocks_for(ns * d), 256, ns, d, c->send_idx.p, x, c->send_buf.p);
@@ -285,80 +285,33 @@ void cheb_sweep(nsb_ctx *c, const CsrDev &M, const double *dinv, const double *b
   if (L == 32) NSB_LAUNCH(c, cheb_sweep_kernel<32>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
 }
 
-int pick_L_nodes(const CsrDev &F) {  // measured on B200: 4 lanes per ~28-entry node row beat 8 and 16
-  const double mean = F.n_rows ? (double)F.nnz / (double)F.n_rows : 0.0;
-  return mean < 48 ? 4 : mean < 96 ? 8 : 16;
-}
-
-// y_u = F x_u (+ A01 x_p)  [mode 0]  or  y = d .* (F x_u)  [mode 3]
-void pad_nodes(nsb_ctx *c, const double *x, double *xpad) {
-  const int64_t nn = c->n_uloc / c->dim;
-  if (c->dim == 2)
-    NSB_LAUNCH(c, pad_nodes_kernel<2>, blocks_for(nn * c->pad), 256, nn, x, xpad);
-  else
-    NSB_LAUNCH(c, pad_nodes_kernel<3>, blocks_for(nn * c->pad), 256, nn, x, xpad);
-}
-
-void fs_apply(nsb_ctx *c, int mode, bool with_a01, const double *xu_std, const double *xp, const double *d, double *y) {
-  pad_nodes(c, xu_std, c->upad.p);
-  const double *xu = c->upad.p;
-  const int L = c->fs_L ? c->fs_L : pick_L_nodes(c->fs);
-  const unsigned grid = blocks_for(c->fs.n_rows * L);
+// y_u = F x_u (+ A01 x_p)  [mode 0]  or  y = d .* (F x_u)  [mode 3], on the slab storage of F_s
+void fs_apply(nsb_ctx *c, int mode, bool with_a01, const double *xu, const double *xp, const double *d, double *y) {
   CsrView a01 = c->a01.view();
   if (!with_a01) a01.rowptr = nullptr;
-#define NSB_FS_CASE(DD, LL, MM) \
-  if (c->dim == DD && L == LL && mode == MM) NSB_LAUNCH(c, (fs_apply_kernel<DD, LL, MM>), grid, 256, c->fs.view(), a01, xu, xp, d, y)
-#define NSB_FS_L(DD, LL) NSB_FS_CASE(DD, LL, 0); NSB_FS_CASE(DD, LL, 3)
-  NSB_FS_L(2, 4);
-  NSB_FS_L(2, 8);
-  NSB_FS_L(2, 16);
-  NSB_FS_L(3, 4);
-  NSB_FS_L(3, 8);
-  NSB_FS_L(3, 16);
-#undef NSB_FS_L
+  const unsigned grid = (unsigned)c->fslab.n_slabs;
+  const SlabView S = c->fslab.view();
+#define NSB_FS_CASE(DD, MM)           \
+  if (c->dim == DD && mode == MM)     \
+  NSB_LAUNCH_SMEM(c, (fs_slab_apply_kernel<DD, MM>), grid, kSlabThreads, c->fslab_smem, S, a01, xu, xp, d, y)
+  NSB_FS_CASE(2, 0);
+  NSB_FS_CASE(2, 3);
+  NSB_FS_CASE(3, 0);
+  NSB_FS_CASE(3, 3);
 #undef NSB_FS_CASE
 }
 
-// mark `ptr` as the persisting L2 window for the next launches on the stream (nullptr: clear)
-void l2_window(nsb_ctx *c, const void *ptr, size_t bytes) {
-  if (!c->l2_persist_bytes) return;
-  cudaStreamAttrValue attr;
-  std::memset(&attr, 0, sizeof(attr));
-  if (ptr) {
-    const size_t win = std::min(bytes, c->l2_window_max);
-    attr.accessPolicyWindow.base_ptr = const_cast<void *>(ptr);
-    attr.accessPolicyWindow.num_bytes = win;
-    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_persist_bytes / (double)win);
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  }
-  if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+void fs_cheb_sweep(nsb_ctx *c, const double *dinv, const double *b, const double *z, double *d, double *znew, double c1,
+                   double c2) {
+  const unsigned grid = (unsigned)c->fslab.n_slabs;
+  const SlabView S = c->fslab.view();
+  if (c->dim == 2)
+    NSB_LAUNCH_SMEM(c, fs_slab_sweep_kernel<2>, grid, kSlabThreads, c->fslab_smem, S, dinv, b, z, d, znew, c1, c2);
+  else
+    NSB_LAUNCH_SMEM(c, fs_slab_sweep_kernel<3>, grid, kSlabThreads, c->fslab_smem, S, dinv, b, z, d, znew, c1, c2);
 }
 
-void fs_cheb_sweep(nsb_ctx *c, const double *dinv, const double *b, const double *zpad, double *d, double *znew,
-                   bool out_std, double c1, double c2) {
-  l2_window(c, zpad, (size_t)(c->n_uloc / c->dim) * c->pad * sizeof(double));
-  const int L = c->fs_L ? c->fs_L : pick_L_nodes(c->fs);
-  const unsigned grid = blocks_for(c->fs.n_rows * L);
-#define NSB_FC_CASE(DD, LL)                                                                                          \
-  if (c->dim == DD && L == LL) {                                                                                     \
-    if (out_std)                                                                                                     \
-      NSB_LAUNCH(c, (fs_cheb_sweep_kernel<DD, LL, true>), grid, 256, c->fs.view(), dinv, b, zpad, d, znew, c1, c2);  \
-    else                                                                                                             \
-      NSB_LAUNCH(c, (fs_cheb_sweep_kernel<DD, LL, false>), grid, 256, c->fs.view(), dinv, b, zpad, d, znew, c1, c2); \
-  }
-  NSB_FC_CASE(2, 4);
-  NSB_FC_CASE(2, 8);
-  NSB_FC_CASE(2, 16);
-  NSB_FC_CASE(3, 4);
-  NSB_FC_CASE(3, 8);
-  NSB_FC_CASE(3, 16);
-#undef NSB_FC_CASE
-  l2_window(c, nullptr, 0);
-}
-
-// vec ~= F^{-1} b: degree-k Chebyshev-Jacobi polynomial on the node-block F, zero initial guess.
-// The iterate lives in padded buffers (gather source); the last sweep writes `out` in standard layout.
+// vec ~= F^{-1} b: degree-k Chebyshev-Jacobi polynomial on F, zero initial guess; the last sweep writes `out`.
 void cheb_solve_F(nsb_ctx *c, const double *b, double *out, double *d, int k, double lmax, double ratio) {
   const int64_t n = c->n_u;
   const double *dinv = c->di.p;
@@ -367,17 +320,14 @@ void cheb_solve_F(nsb_ctx *c, const double *b, double *out, double *d, int k, do
     NSB_LAUNCH(c, cheb_first_kernel, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, out);
     return;
   }
-  double *z = c->zpadA.p, *zn = c->zpadB.p;
-  if (c->dim == 2)
-    NSB_LAUNCH(c, fs_cheb_first_kernel<2>, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, z);
-  else
-    NSB_LAUNCH(c, fs_cheb_first_kernel<3>, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, z);
+  double *z = c->chzA.p, *zn = c->chzB.p;
+  NSB_LAUNCH(c, cheb_first_kernel, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, z);
   double rho = 1.0 / sigma;
   for (int i = 1; i < k; ++i) {
     const double rho_new = 1.0 / (2.0 * sigma - rho);
     const bool last = i == k - 1;
-    halo_exchange(c, z, c->pad);
-    fs_cheb_sweep(c, dinv, b, z, d, last ? out : zn, last, rho_new * rho, 2.0 * rho_new / delta);
+    halo_exchange(c, z);
+    fs_cheb_sweep(c, dinv, b, z, d, last ? out : zn, rho_new * rho, 2.0 * rho_new / delta);
     std::swap(z, zn);
     rho = rho_new;
   }
@@ -535,6 +485,31 @@ void materialize_canonical_values(nsb_ctx *c) {
                c->fs.val.p, c->a00.val.p);
 }
 
+// Slab form of F_s (slab.cuh).  The window capacity keeps 6 CTAs of 256 threads resident per SM
+// (6 x (dim*8*cap + 1 KB) <= 227 KB).
+void build_fslab(nsb_ctx *c) {
+  const CsrDev &F = c->fs;
+  std::vector<int64_t> rp((size_t)F.n_rows + 1);
+  std::vector<uint32_t> ci((size_t)F.nnz);
+  F.rowptr.download(rp.data(), c->stream);
+  F.colind.download(ci.data(), c->stream);
+  uint32_t cap = c->dim == 3 ? 1408u : 2112u;
+  if (const char *e = std::getenv("NSB_SLAB_WINDOW")) cap = (uint32_t)std::max(64, std::atoi(e));
+  const SlabHost H = build_slabs(F.n_rows, c->n_uloc / c->dim, rp.data(), ci.data(), cap);
+  upload_slabs(H, F.n_rows, c->fslab, c->stream, &c->dev_bytes);
+  c->fslab_smem = sizeof(double) * c->dim * std::max<size_t>(c->fslab.max_window, kSlabThreads);
+  auto prep = [&](const void *f) {
+    NSB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fslab_smem));
+    NSB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  };
+  prep((const void *)fs_slab_apply_kernel<2, 0>);
+  prep((const void *)fs_slab_apply_kernel<2, 3>);
+  prep((const void *)fs_slab_apply_kernel<3, 0>);
+  prep((const void *)fs_slab_apply_kernel<3, 3>);
+  prep((const void *)fs_slab_sweep_kernel<2>);
+  prep((const void *)fs_slab_sweep_kernel<3>);
+}
+
 void finalize_setup(nsb_ctx *c) {
   if (c->finalized) return;
   if (!c->have_mesh || !c->have_dofs || !c->fs.have || !c->a01.have || !c->a10.have)
@@ -584,19 +559,6 @@ void finalize_setup(nsb_ctx *c) {
   dz(c->tmpN, N);
   dz(c->pz, N);
   if (const char *e = std::getenv("NSB_GRAPH")) c->use_graph = std::atoi(e) != 0;
-  {
-    const char *e = std::getenv("NSB_L2_PERSIST");
-    cudaDeviceProp prop;
-    if ((e && std::atoi(e) != 0) && cudaGetDeviceProperties(&prop, c->device) == cudaSuccess &&
-        prop.persistingL2CacheMaxSize > 0) {
-      const size_t want = (size_t)prop.persistingL2CacheMaxSize;
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-        c->l2_persist_bytes = want;
-        c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-      } else
-        cudaGetLastError();
-    }
-  }
   dz(c->hdev, 2 * kMaxDots + 8);
   dz(c->partials, (size_t)kMaxDots * kRedBlocks);
   dz(c->coef, kMaxDots);
@@ -615,19 +577,11 @@ void finalize_setup(nsb_ctx *c) {
   dz(c->eig_w, std::max<int64_t>(c->n_uloc, c->n_p));
   dz(c->force_out, 2);
   dz(c->mdiag, (size_t)c->n_own_nodes);
-  c->pad = c->dim == 3 ? 4 : 2;
-  {
-    const size_t np_ = (size_t)(c->n_uloc / c->dim) * c->pad;
-    dz(c->upad, np_);
-    dz(c->zpadA, np_);
-    dz(c->zpadB, np_);
-    if (c->send_ptr.size() > 1 && c->send_ptr.back() > 0)
-      c->send_buf.alloc((size_t)c->send_ptr.back() * std::max(c->dim, c->pad), &c->dev_bytes);
-  }
-  if (const char *e = std::getenv("NSB_FS_L")) {
-    const int L = std::atoi(e);
-    if (L == 4 || L == 8 || L == 16) c->fs_L = L;
-  }
+  dz(c->chzA, c->n_uloc);
+  dz(c->chzB, c->n_uloc);
+  if (c->send_ptr.size() > 1 && c->send_ptr.back() > 0)
+    c->send_buf.alloc((size_t)c->send_ptr.back() * c->dim, &c->dev_bytes);
+  build_fslab(c);
   if (c->dim == 2)
     NSB_LAUNCH(c, mass_diag_kernel<2>, blocks_for(c->n_cells), 256, c->n_cells, c->xyz.p, c->cell_verts.p,
                c->cell_nodes.p, c->n_own_nodes, c->fe.p, c->mdiag.p);
@@ -703,6 +657,9 @@ void assemble_launch(nsb_ctx *c) {
       NSB_LAUNCH(c, apply_dirichlet_kernel<3>, blocks_for(nb * 32), 256, nb, c->bc_nodes.p, c->bc_vals.p, c->bc_factor,
                  c->fs.view(), c->a01.view(), c->diagF.p, c->first_diag.p, c->bc_mode, c->rhs.p, c->sol.p);
   }
+  // the solver streams F_s in slab order
+  NSB_LAUNCH(c, slab_repack_kernel, blocks_for(c->fslab.padded), 256, c->fslab.padded, c->fslab.src.p, c->fs.val.p,
+             c->fslab.val.p);
 }
 
 // ---- preconditioner -------------------------------------------------------
@@ -1528,7 +1485,7 @@ int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
           NSB_LAUNCH(c, schur_outer_kernel, blocks_for((int64_t)c->n_u * 32), 256, c->a01.view(), c->a10t.p, c->di.p,
                      c->s.view());
           break;
-        case 4: fs_cheb_sweep(c, c->di.p, c->rhs.p, c->zpadA.p, c->chd_u.p, c->zpadB.p, false, 0.5, 0.5); break;
+        case 4: fs_cheb_sweep(c, c->di.p, c->rhs.p, c->chzA.p, c->chd_u.p, c->chzB.p, 0.5, 0.5); break;
         case 6: cheb_sweep(c, c->s, c->dis.p, c->vec1.p, c->chz_p.p, c->chd_p.p, c->chz_p2.p, 0.5, 0.5); break;
         default: throw ArgError("nsb_bench_kernel: unknown kernel id");
       }
@@ -1548,7 +1505,7 @@ int nsb_timers(const nsb_ctx *c, double out_ms[4]) {
   for (int i = 0; i < 4; ++i) out_ms[i] = c->t_ms[i];
   return NSB_OK;
 }
-int nsb_info(const nsb_ctx *c, int64_t out[13]) {
+int nsb_info(const nsb_ctx *c, int64_t out[16]) {
   if (!c) return NSB_EARG;
   out[0] = c->n_u;
   out[1] = c->n_p;
@@ -1563,7 +1520,56 @@ int nsb_info(const nsb_ctx *c, int64_t out[13]) {
   out[10] = c->schur_mode == 1 ? 2 * c->amg_nu * c->amg_cycles : c->kS;
   out[11] = c->schur_mode;
   out[12] = (int64_t)c->amg.size();
+  out[13] = c->fslab.padded;
+  out[14] = (int64_t)c->fslab.win_list.n;
+  out[15] = c->fslab.n_slabs;
   return NSB_OK;
+}
+
+int nsb_slab_host_check(int dim, int64_t n_rows, int64_t n_cols, const int64_t *rowptr, const uint32_t *colind,
+                        const double *val, uint32_t window_cap, const double *x, double *y, int64_t stats[5]) {
+  try {
+    if ((dim != 2 && dim != 3) || !rowptr || !colind || !val || !x || !y || !stats) return NSB_EARG;
+    const SlabHost H = build_slabs(n_rows, n_cols, rowptr, colind, window_cap);
+    const int64_t ns = (int64_t)H.slab_row.size() - 1;
+    std::vector<double> win, part((size_t)kSlabThreads * dim);
+    for (int64_t s = 0; s < ns; ++s) {
+      // what slab_product does: stage the window, one partial sum per thread, fixed-order row sums
+      const uint32_t w0 = H.win_ptr[s], nw = H.win_ptr[s + 1] - w0;
+      win.resize((size_t)nw * dim);
+      for (uint32_t i = 0; i < nw * (uint32_t)dim; ++i) win[i] = x[(size_t)dim * H.win_list[w0 + i / dim] + i % dim];
+      for (int t = 0; t < kSlabThreads; ++t) {
+        const int64_t sl = s * kSlabSlices + (t >> 5), base = H.slice_ptr[sl];
+        const int W = (int)((H.slice_ptr[sl + 1] - base) >> 5);
+        for (int c = 0; c < dim; ++c) part[(size_t)t * dim + c] = 0.0;
+        for (int k = 0; k < W; ++k) {
+          const int64_t p = base + 32 * (int64_t)k + (t & 31);
+          const double a = H.src[p] != kSlabPad ? val[H.src[p]] : 0.0;
+          if (H.idx[p] >= std::max<uint32_t>(nw, 1)) return NSB_ESTRUCT;
+          for (int c = 0; c < dim; ++c) part[(size_t)t * dim + c] += a * win[(size_t)dim * H.idx[p] + c];
+        }
+      }
+      for (uint32_t r = H.slab_row[s]; r < H.slab_row[s + 1]; ++r)
+        for (int c = 0; c < dim; ++c) {
+          const uint32_t vp = H.vpos[r];
+          double sum = part[(size_t)dim * (vp & 0x3ffu) + c];
+          const uint32_t p1 = (vp >> 10) & 0x3ffu, p2 = (vp >> 20) & 0x3ffu;
+          if (p1 != kVposNone) sum += part[(size_t)dim * p1 + c];
+          if (p2 != kVposNone) sum += part[(size_t)dim * p2 + c];
+          y[(size_t)dim * r + c] = sum;
+        }
+    }
+    stats[0] = ns;
+    stats[1] = H.nnz;
+    stats[2] = H.slice_ptr.back();
+    stats[3] = H.max_window;
+    stats[4] = (int64_t)H.win_list.size();
+    return NSB_OK;
+  } catch (const StructError &) {
+    return NSB_ESTRUCT;
+  } catch (...) {
+    return NSB_EARG;
+  }
 }
 
 void *nsb_alloc_pinned(int64_t bytes) {

@@ -1,0 +1,306 @@
+// Slab storage of the node-level velocity block F_s (A00 = F_s (x) I_dim) and the
+// kernels that stream it: the velocity rows of y = A x (GMRES, reference
+// src/NavierStokes.cpp:377) and the Jacobi-type inner sweep on F that replaces
+// the ILU-preconditioned inner GMRES of PreconditionASIMPLE::vmult (:978-981).
+//
+// Why not CSR.  With 12 B per stored non-zero for 2*dim flops the node-block CSR
+// kernels were bound by the GATHER, not by the matrix stream: every non-zero
+// pulled a 32-byte sector of the vector through L1/L2 (ncu, round 1: L1/LSU the
+// busiest unit, 91 % long-scoreboard stalls, 34 % of the HBM roofline), and rows
+// of 18 / 27 / 65 entries (edge / face-adjacent / vertex nodes) left most lanes
+// of a sub-warp-per-row kernel idle.
+//
+// Layout.  Consecutive rows are grouped into slabs of at most kSlabThreads
+// *virtual rows* (a row longer than ~1.4x the mean is cut into <= 3 chunks of
+// equal length so that all virtual rows have similar lengths).  Per slab:
+//   * a WINDOW: the sorted list of distinct column nodes of its rows
+//     (~3-4 per row).  The kernel stages the dim values of every window node in
+//     shared memory once, with coalesced loads, so every vector sector is
+//     fetched once per slab instead of once per non-zero;
+//   * the virtual rows sorted by length and stored as 8 ELL slices of 32 rows
+//     (column-major inside a slice): thread t of the CTA owns virtual row t and
+//     streams `val` (8 B) and a 16-bit window-local column index (2 B) with
+//     perfectly coalesced 256 B + 64 B warp loads -- 10 B per non-zero instead
+//     of 12 B, no row pointers, no shuffles;
+//   * per real row a packed word with the thread positions of its <= 3 chunks;
+//     partial sums are combined in a fixed order (deterministic) in the
+//     coalesced epilogue that also applies the vector update of the sweep.
+// The CSR values stay the assembly target (scatter by slot); `slab_repack_kernel`
+// copies them into the ELL order once per time step through a precomputed map.
+#pragma once
+#include <algorithm>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace nsb {
+
+constexpr int kSlabThreads = 256;  // virtual rows (= threads) per slab
+constexpr int kSlabSlices = kSlabThreads / 32;
+constexpr int kSlabMaxChunks = 3;
+constexpr uint32_t kVposNone = 0x3ffu;
+constexpr uint32_t kSlabPad = 0xffffffffu;
+
+struct SlabView {
+  int n_slabs;
+  const uint32_t *slab_row;  // n_slabs+1: first real row of every slab
+  const uint32_t *win_ptr;   // n_slabs+1: offsets into win_list
+  const uint32_t *win_list;  // window nodes, ascending inside a slab
+  const int64_t *slice_ptr;  // n_slabs*kSlabSlices+1: offsets into val/idx (multiples of 32)
+  const double *val;
+  const uint16_t *idx;
+  const uint32_t *vpos;      // per real row: 3 x 10-bit thread positions of its chunks (kVposNone = unused)
+};
+
+struct SlabHost {
+  std::vector<uint32_t> slab_row, win_ptr, win_list, vpos, src;
+  std::vector<int64_t> slice_ptr;
+  std::vector<uint16_t> idx;
+  uint32_t max_window = 0;
+  int64_t nnz = 0;
+};
+
+struct SlabDev {
+  int n_slabs = 0;
+  int64_t n_rows = 0, nnz = 0, padded = 0;
+  uint32_t max_window = 0;
+  DevBuf<uint32_t> slab_row, win_ptr, win_list, vpos, src;
+  DevBuf<int64_t> slice_ptr;
+  DevBuf<double> val;
+  DevBuf<uint16_t> idx;
+  bool have = false;
+  SlabView view() const {
+    return {n_slabs, slab_row.p, win_ptr.p, win_list.p, slice_ptr.p, val.p, idx.p, vpos.p};
+  }
+  size_t window_total() const { return win_list.n; }
+};
+
+// Host construction from the CSR pattern (once per setup).  window_cap: largest
+// window (in nodes) a slab may have -- it bounds the shared memory of the kernels.
+inline SlabHost build_slabs(int64_t n_rows, int64_t n_cols, const int64_t *rp, const uint32_t *ci, uint32_t window_cap) {
+  SlabHost H;
+  H.nnz = rp[n_rows];
+  if (H.nnz >= (int64_t)kSlabPad) throw ArgError("slab storage: more than 2^32-2 stored entries per rank");
+  const double mean = n_rows ? (double)H.nnz / (double)n_rows : 1.0;
+  const int target = std::max(8, (int)std::lround(0.85 * mean));
+  auto n_chunks = [&](int64_t len) {
+    return (int)std::min<int64_t>(kSlabMaxChunks, std::max<int64_t>(1, (len + target / 2) / target));
+  };
+  // pass 1 (sequential): slab boundaries and unsorted windows
+  std::vector<int32_t> stamp((size_t)n_cols, -1);
+  H.slab_row.push_back(0);
+  H.win_ptr.push_back(0);
+  H.win_list.reserve((size_t)n_rows * 4);
+  int32_t slab = 0;
+  int vcount = 0;
+  uint32_t wcount = 0;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int64_t b = rp[r], e = rp[r + 1];
+    if ((uint64_t)(e - b) > window_cap) throw StructError("slab storage: a row has more entries than the window capacity");
+    const int nch = n_chunks(e - b);
+    uint32_t fresh = 0;
+    for (int64_t k = b; k < e; ++k) fresh += stamp[ci[k]] != slab;
+    if (vcount > 0 && (vcount + nch > kSlabThreads || wcount + fresh > window_cap)) {
+      H.slab_row.push_back((uint32_t)r);
+      H.win_ptr.push_back((uint32_t)H.win_list.size());
+      ++slab;
+      vcount = 0;
+      wcount = 0;
+    }
+    for (int64_t k = b; k < e; ++k)
+      if (stamp[ci[k]] != slab) {
+        stamp[ci[k]] = slab;
+        H.win_list.push_back(ci[k]);
+        ++wcount;
+      }
+    vcount += nch;
+  }
+  H.slab_row.push_back((uint32_t)n_rows);
+  H.win_ptr.push_back((uint32_t)H.win_list.size());
+  const int64_t ns = (int64_t)H.slab_row.size() - 1;
+  // pass 2 (parallel): sort windows, sort virtual rows by length, slice widths
+  struct VRow {
+    uint32_t row;
+    uint16_t off, len;  // chunk = entries [rp[row]+off, +len)
+    uint16_t chunk;     // position among the chunks of the row
+  };
+  std::vector<std::vector<VRow>> vrows((size_t)ns);
+  std::vector<int64_t> slice_len((size_t)ns * kSlabSlices, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t s = 0; s < ns; ++s) {
+    std::sort(H.win_list.begin() + H.win_ptr[s], H.win_list.begin() + H.win_ptr[s + 1]);
+    std::vector<VRow> &v = vrows[s];
+    for (uint32_t r = H.slab_row[s]; r < H.slab_row[s + 1]; ++r) {
+      const int64_t len = rp[r + 1] - rp[r];
+      const int nch = n_chunks(len);
+      int64_t off = 0;
+      for (int j = 0; j < nch; ++j) {
+        const int64_t l = (len - off + (nch - j) - 1) / (nch - j);
+        v.push_back({r, (uint16_t)off, (uint16_t)l, (uint16_t)j});
+        off += l;
+      }
+    }
+    std::stable_sort(v.begin(), v.end(), [](const VRow &a, const VRow &b) { return a.len > b.len; });
+    for (int w = 0; w < kSlabSlices; ++w)
+      slice_len[s * kSlabSlices + w] = (size_t)w * 32 < v.size() ? 32 * (int64_t)v[(size_t)w * 32].len : 0;
+  }
+  H.slice_ptr.assign((size_t)ns * kSlabSlices + 1, 0);
+  for (size_t i = 0; i < slice_len.size(); ++i) H.slice_ptr[i + 1] = H.slice_ptr[i] + slice_len[i];
+  const int64_t total = H.slice_ptr.back();
+  H.idx.assign((size_t)total, 0);
+  H.src.assign((size_t)total, kSlabPad);
+  H.vpos.assign((size_t)n_rows, kVposNone | (kVposNone << 10) | (kVposNone << 20));
+  uint32_t maxw = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : maxw)
+  for (int64_t s = 0; s < ns; ++s) {
+    const uint32_t *wb = H.win_list.data() + H.win_ptr[s], *we = H.win_list.data() + H.win_ptr[s + 1];
+    maxw = std::max(maxw, (uint32_t)(we - wb));
+    const std::vector<VRow> &v = vrows[s];
+    for (size_t t = 0; t < v.size(); ++t) {
+      const VRow &q = v[t];
+      const int64_t base = H.slice_ptr[s * kSlabSlices + (int64_t)(t >> 5)] + (int64_t)(t & 31);
+      for (int k = 0; k < q.len; ++k) {
+        const int64_t p = rp[q.row] + q.off + k;
+        H.idx[(size_t)(base + 32 * (int64_t)k)] = (uint16_t)(std::lower_bound(wb, we, ci[p]) - wb);
+        H.src[(size_t)(base + 32 * (int64_t)k)] = (uint32_t)p;
+      }
+      uint32_t &vp = H.vpos[q.row];  // the chunks of a row live in one slab: no race across threads
+      const int slot = q.chunk;
+      vp = (vp & ~(0x3ffu << (10 * slot))) | ((uint32_t)t << (10 * slot));
+    }
+  }
+  H.max_window = maxw;
+  return H;
+}
+
+inline void upload_slabs(const SlabHost &H, int64_t n_rows, SlabDev &D, cudaStream_t s, int64_t *bytes) {
+  D.n_slabs = (int)H.slab_row.size() - 1;
+  D.n_rows = n_rows;
+  D.nnz = H.nnz;
+  D.padded = H.slice_ptr.back();
+  D.max_window = H.max_window;
+  D.slab_row.upload(H.slab_row.data(), H.slab_row.size(), s, bytes);
+  D.win_ptr.upload(H.win_ptr.data(), H.win_ptr.size(), s, bytes);
+  D.win_list.upload(H.win_list.data(), H.win_list.size(), s, bytes);
+  D.vpos.upload(H.vpos.data(), H.vpos.size(), s, bytes);
+  D.src.upload(H.src.data(), H.src.size(), s, bytes);
+  D.slice_ptr.upload(H.slice_ptr.data(), H.slice_ptr.size(), s, bytes);
+  D.idx.upload(H.idx.data(), H.idx.size(), s, bytes);
+  D.val.alloc((size_t)D.padded, bytes);
+  D.val.zero(s);
+  NSB_CUDA(cudaStreamSynchronize(s));
+  D.have = true;
+}
+
+// ELL values from the CSR values (after assembly and boundary rows), padding = 0
+__global__ void slab_repack_kernel(int64_t n, const uint32_t *__restrict__ src, const double *__restrict__ csr_val,
+                                   double *__restrict__ ell_val) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint32_t p = __ldcs(src + i);
+    ell_val[i] = p != kSlabPad ? csr_val[p] : 0.0;
+  }
+}
+
+// Stage the window of slab s in shared memory and form this thread's partial row sum.
+template <int DIM>
+__device__ __forceinline__ void slab_product(const SlabView &S, int s, const double *__restrict__ x, double *sm,
+                                             double (&acc)[DIM]) {
+  const int t = threadIdx.x;
+  const uint32_t w0 = S.win_ptr[s], nw = S.win_ptr[s + 1] - w0;
+  for (uint32_t i = t; i < DIM * nw; i += kSlabThreads) {
+    const uint32_t node = __ldg(S.win_list + w0 + i / DIM);
+    sm[i] = __ldg(x + (size_t)DIM * node + i % DIM);
+  }
+  const int64_t sl = (int64_t)s * kSlabSlices + (t >> 5);
+  const int64_t base = S.slice_ptr[sl];
+  const int W = (int)((S.slice_ptr[sl + 1] - base) >> 5);
+  const double *__restrict__ v = S.val + base + (t & 31);
+  const uint16_t *__restrict__ ix = S.idx + base + (t & 31);
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) acc[c] = 0.0;
+  __syncthreads();
+  int k = 0;
+  for (; k + 4 <= W; k += 4) {
+    double a[4];
+    unsigned j[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a[u] = __ldcs(v + 32 * (k + u));
+      j[u] = __ldcs(ix + 32 * (k + u));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) acc[c] += a[u] * sm[DIM * j[u] + c];
+  }
+  for (; k < W; ++k) {
+    const double a = __ldcs(v + 32 * k);
+    const unsigned j = __ldcs(ix + 32 * k);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) acc[c] += a * sm[DIM * j + c];
+  }
+  __syncthreads();  // every warp is done with the window: its space now takes the partial sums
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) sm[DIM * t + c] = acc[c];
+  __syncthreads();
+}
+
+// (F x)[row r of the slab][component c] from the partial sums in shared memory, fixed order
+template <int DIM>
+__device__ __forceinline__ double slab_row_sum(const double *sm, uint32_t vp, int c) {
+  double s = sm[DIM * (vp & 0x3ffu) + c];
+  const uint32_t p1 = (vp >> 10) & 0x3ffu, p2 = (vp >> 20) & 0x3ffu;
+  if (p1 != kVposNone) s += sm[DIM * p1 + c];
+  if (p2 != kVposNone) s += sm[DIM * p2 + c];
+  return s;
+}
+
+// velocity rows of the block product:  y_u = F x_u (+ A01 x_p when a01.rowptr)
+//   MODE 0: y = ..., MODE 3: y = d .* (F x)   (power iteration on D^-1 F)
+template <int DIM, int MODE>
+__global__ void __launch_bounds__(kSlabThreads) fs_slab_apply_kernel(SlabView S, CsrView a01,
+                                                                     const double *__restrict__ xu,
+                                                                     const double *__restrict__ xp,
+                                                                     const double *__restrict__ d,
+                                                                     double *__restrict__ y) {
+  extern __shared__ double sm[];
+  const int s = blockIdx.x;
+  double acc[DIM];
+  slab_product<DIM>(S, s, xu, sm, acc);
+  const uint32_t r0 = S.slab_row[s], nr = S.slab_row[s + 1] - r0;
+  for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
+    const uint32_t r = i / DIM;
+    double sc = slab_row_sum<DIM>(sm, S.vpos[r0 + r], (int)(i % DIM));
+    const int64_t g = (int64_t)DIM * r0 + i;
+    if (MODE == 0 && a01.rowptr != nullptr) {
+      const int64_t b = a01.rowptr[g], e = a01.rowptr[g + 1];
+      for (int64_t k = b; k < e; ++k) sc += __ldcs(a01.val + k) * __ldg(xp + __ldcs(a01.colind + k));
+    }
+    y[g] = MODE == 3 ? d[g] * sc : sc;
+  }
+}
+
+// One Chebyshev-Jacobi sweep on F z = b (see cheb_sweep_kernel in spmv.cuh):
+//   dnew = c1 * d + c2 * Dinv .* (b - F z);  znew = z + dnew      (z, znew distinct)
+template <int DIM>
+__global__ void __launch_bounds__(kSlabThreads) fs_slab_sweep_kernel(SlabView S, const double *__restrict__ dinv,
+                                                                     const double *__restrict__ b,
+                                                                     const double *__restrict__ z,
+                                                                     double *__restrict__ d, double *__restrict__ znew,
+                                                                     double c1, double c2) {
+  extern __shared__ double sm[];
+  const int s = blockIdx.x;
+  double acc[DIM];
+  slab_product<DIM>(S, s, z, sm, acc);
+  const uint32_t r0 = S.slab_row[s], nr = S.slab_row[s + 1] - r0;
+  for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
+    const double sc = slab_row_sum<DIM>(sm, S.vpos[r0 + i / DIM], (int)(i % DIM));
+    const int64_t g = (int64_t)DIM * r0 + i;
+    const double dn = c1 * d[g] + c2 * dinv[g] * (b[g] - sc);
+    d[g] = dn;
+    znew[g] = __ldg(z + g) + dn;
+  }
+}
+
+}  // namespace nsb

@@ -109,171 +109,6 @@ __global__ void __launch_bounds__(256) cheb_sweep_kernel(CsrView M, const double
   }
 }
 
-// ---------------------------------------------------------------------------
-// Node-block form of the velocity block: A00 = F_s (x) I_dim, stored as the
-// scalar node-level CSR F_s.  Per stored non-zero 12 B are streamed for 2*dim
-// flops instead of 12*dim^2 B in the canonical block.
-//
-// The vector that is GATHERED is kept in a padded node layout [node][PAD],
-// PAD = 4 in 3D (2 in 2D), so that the dim values of a neighbour node sit in
-// one aligned 32-byte sector and are fetched by one 128-bit + one 64-bit load.
-// (ncu on the unpadded version: 1.75 sectors and 3 load instructions per
-// non-zero made L1/LSU the busiest unit at 64 %, DRAM at 34 %.)
-// ---------------------------------------------------------------------------
-template <int DIM>
-struct NodePad {
-  static constexpr int value = DIM == 3 ? 4 : 2;
-};
-
-template <int DIM>
-__device__ __forceinline__ void gather_node(const double *__restrict__ xpad, uint32_t col, double (&v)[DIM]) {
-  const double2 *p = reinterpret_cast<const double2 *>(xpad + (size_t)NodePad<DIM>::value * col);
-  const double2 a = __ldg(p);
-  v[0] = a.x;
-  v[1] = a.y;
-  if constexpr (DIM == 3) v[2] = __ldg(reinterpret_cast<const double *>(p + 1));
-}
-
-template <int DIM, int L>
-__device__ __forceinline__ void node_row_dot(const CsrView &F, int64_t node, const double *__restrict__ xpad, int sub,
-                                             double (&s)[DIM]) {
-  const int64_t b = __ldg(F.rowptr + node), e = __ldg(F.rowptr + node + 1);
-  double t[DIM];
-#pragma unroll
-  for (int c = 0; c < DIM; ++c) t[c] = 0.0;
-  int64_t k = b + sub;
-  // four entries per lane in flight: all (value, column) loads first, then the four gathers
-  for (; k + 3 * L < e; k += 4 * L) {
-    const double v0 = ld_stream(F.val + k), v1 = ld_stream(F.val + k + L);
-    const double v2 = ld_stream(F.val + k + 2 * L), v3 = ld_stream(F.val + k + 3 * L);
-    const uint32_t c0 = ld_stream(F.colind + k), c1 = ld_stream(F.colind + k + L);
-    const uint32_t c2 = ld_stream(F.colind + k + 2 * L), c3 = ld_stream(F.colind + k + 3 * L);
-    double x0[DIM], x1[DIM], x2[DIM], x3[DIM];
-    gather_node<DIM>(xpad, c0, x0);
-    gather_node<DIM>(xpad, c1, x1);
-    gather_node<DIM>(xpad, c2, x2);
-    gather_node<DIM>(xpad, c3, x3);
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) {
-      s[c] += v0 * x0[c];
-      t[c] += v1 * x1[c];
-      s[c] += v2 * x2[c];
-      t[c] += v3 * x3[c];
-    }
-  }
-  for (; k + L < e; k += 2 * L) {
-    const double v0 = ld_stream(F.val + k), v1 = ld_stream(F.val + k + L);
-    const uint32_t c0 = ld_stream(F.colind + k), c1 = ld_stream(F.colind + k + L);
-    double x0[DIM], x1[DIM];
-    gather_node<DIM>(xpad, c0, x0);
-    gather_node<DIM>(xpad, c1, x1);
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) {
-      s[c] += v0 * x0[c];
-      t[c] += v1 * x1[c];
-    }
-  }
-  if (k < e) {
-    const double v0 = ld_stream(F.val + k);
-    double x0[DIM];
-    gather_node<DIM>(xpad, ld_stream(F.colind + k), x0);
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) s[c] += v0 * x0[c];
-  }
-#pragma unroll
-  for (int c = 0; c < DIM; ++c) s[c] += t[c];
-}
-
-// standard [node][dim] -> padded [node][PAD] (all local nodes incl. ghosts)
-template <int DIM>
-__global__ void pad_nodes_kernel(int64_t n_nodes, const double *__restrict__ x, double *__restrict__ xpad) {
-  constexpr int PAD = NodePad<DIM>::value;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_nodes * PAD) return;
-  const int64_t node = t / PAD;
-  const int c = (int)(t % PAD);
-  xpad[t] = c < DIM ? x[node * DIM + c] : 0.0;
-}
-
-// velocity rows of the block product:  y_u = F x_u (+ A01 x_p when a01.rowptr)
-//   MODE 0: y = ..., MODE 3: y = d .* (F x)   (power iteration on D^-1 F)
-template <int DIM, int L, int MODE>
-__global__ void __launch_bounds__(256) fs_apply_kernel(CsrView F, CsrView a01, const double *__restrict__ xpad,
-                                                       const double *__restrict__ xp, const double *__restrict__ d,
-                                                       double *__restrict__ y) {
-  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
-  const int sub = threadIdx.x % L;
-  const bool live = g < F.n_rows;
-  double s[DIM];
-#pragma unroll
-  for (int c = 0; c < DIM; ++c) s[c] = 0.0;
-  if (live) {
-    node_row_dot<DIM, L>(F, g, xpad, sub, s);
-    if (a01.rowptr != nullptr) {
-#pragma unroll
-      for (int c = 0; c < DIM; ++c) s[c] += row_dot<L>(a01, (int64_t)DIM * g + c, xp, sub);
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < DIM; ++c) s[c] = sub_reduce<L>(s[c]);
-  if (live && sub < DIM) {
-    double sc = s[0];
-#pragma unroll
-    for (int c = 1; c < DIM; ++c)
-      if (sub == c) sc = s[c];
-    const int64_t i = (int64_t)DIM * g + sub;
-    y[i] = MODE == 3 ? d[i] * sc : sc;
-  }
-}
-
-// Chebyshev-Jacobi sweep on F (see cheb_sweep_kernel), node-block form.  z is
-// padded; the result goes to a padded buffer (next sweep) or, for the last
-// sweep, to a standard-layout vector.
-template <int DIM, int L, bool OUT_STD>
-__global__ void __launch_bounds__(256) fs_cheb_sweep_kernel(CsrView F, const double *__restrict__ dinv,
-                                                            const double *__restrict__ b,
-                                                            const double *__restrict__ zpad, double *__restrict__ d,
-                                                            double *__restrict__ znew, double c1, double c2) {
-  constexpr int PAD = NodePad<DIM>::value;
-  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
-  const int sub = threadIdx.x % L;
-  const bool live = g < F.n_rows;
-  double s[DIM];
-#pragma unroll
-  for (int c = 0; c < DIM; ++c) s[c] = 0.0;
-  if (live) node_row_dot<DIM, L>(F, g, zpad, sub, s);
-#pragma unroll
-  for (int c = 0; c < DIM; ++c) s[c] = sub_reduce<L>(s[c]);
-  if (live && sub < DIM) {
-    // lane c of the sub-warp finishes component c
-    double sc = s[0];
-#pragma unroll
-    for (int c = 1; c < DIM; ++c)
-      if (sub == c) sc = s[c];
-    const int64_t i = (int64_t)DIM * g + sub;
-    const double dn = c1 * d[i] + c2 * dinv[i] * (b[i] - sc);
-    d[i] = dn;
-    const double zn = zpad[(int64_t)PAD * g + sub] + dn;
-    if (OUT_STD)
-      znew[i] = zn;
-    else
-      znew[(int64_t)PAD * g + sub] = zn;
-  }
-}
-
-// first sweep on F with zero initial guess: d = Dinv .* b / theta (standard), z = d (padded)
-template <int DIM>
-__global__ void fs_cheb_first_kernel(int64_t n_u, const double *__restrict__ dinv, const double *__restrict__ b,
-                                     double inv_theta, double *__restrict__ d, double *__restrict__ zpad) {
-  constexpr int PAD = NodePad<DIM>::value;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_u) {
-    const double v = dinv[i] * b[i] * inv_theta;
-    d[i] = v;
-    zpad[(i / DIM) * PAD + i % DIM] = v;
-  }
-}
-
 // first sweep with zero initial guess: d = z = Dinv .* b / theta
 __global__ void cheb_first_kernel(int64_t n, const double *__restrict__ dinv, const double *__restrict__ b,
                                   double inv_theta, double *__restrict__ d, double *__restrict__ z) {
@@ -322,7 +157,7 @@ __global__ void __launch_bounds__(256) schur_outer_kernel(CsrView Bt, const doub
   }
 }
 
-// halo pack: buf[i][c] = x[width*idx[i] + c], width = dim (standard) or PAD (padded vectors)
+// halo pack: buf[i][c] = x[width*idx[i] + c], width = dim
 __global__ void halo_pack_kernel(int64_t n, int width, const uint32_t *__restrict__ idx, const double *__restrict__ x,
                                  double *__restrict__ buf) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

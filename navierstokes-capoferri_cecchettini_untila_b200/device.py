@@ -22,6 +22,7 @@ SYMBOLS = [
     "nsb_compute_forces", "nsb_get_matrix_values", "nsb_get_pattern", "nsb_nnz", "nsb_get_rhs", "nsb_vmult",
     "nsb_bench_kernel", "nsb_launch_count", "nsb_timers", "nsb_info", "nsb_alloc_pinned", "nsb_free_pinned",
     "nsb_comm_unique_id", "nsb_comm_init", "nsb_set_local_dofs", "nsb_set_halo", "nsb_set_schur_solver", "nsb_gather_velocity",
+    "nsb_slab_host_check",
 ]
 
 
@@ -81,12 +82,32 @@ def device_lib():
         L.nsb_set_local_dofs.argtypes = [p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p, u32p]
         L.nsb_set_halo.argtypes = [p, C.c_int, i32p, i64p, u32p, i64p]
         L.nsb_gather_velocity.argtypes = [p, u32p, f64p]
+        L.nsb_slab_host_check.argtypes = [C.c_int, C.c_int64, C.c_int64, i64p, u32p, f64p, C.c_uint32, f64p, f64p, i64p]
         _lib = L
     return _lib
 
 
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
+
+
+def slab_host_check(dim, rowptr, colind, val, x, n_cols=None, window_cap=1408):
+    """Host evaluation of y = (F_s (x) I_dim) x through the slab layout of csrc/slab.cuh
+    (no device needed).  Returns (y, stats dict)."""
+    rowptr = np.ascontiguousarray(rowptr, np.int64)
+    colind = np.ascontiguousarray(colind, np.uint32)
+    val = np.ascontiguousarray(val, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    n_rows = rowptr.size - 1
+    n_cols = n_rows if n_cols is None else n_cols
+    y = np.zeros(dim * n_rows)
+    st = np.zeros(5, np.int64)
+    rc = device_lib().nsb_slab_host_check(dim, n_rows, n_cols, _p(rowptr, C.c_int64), _p(colind, C.c_uint32),
+                                          _p(val, C.c_double), window_cap, _p(x, C.c_double), _p(y, C.c_double),
+                                          _p(st, C.c_int64))
+    if rc != 0:
+        raise DeviceError(f"nsb_slab_host_check failed ({rc})")
+    return y, dict(zip(["slabs", "nnz", "padded", "max_window", "window_total"], [int(v) for v in st]))
 
 
 class Device:
@@ -282,8 +303,8 @@ class Device:
         return out
 
     def info(self):
-        out = (C.c_int64 * 13)()
+        out = (C.c_int64 * 16)()
         self._chk(self.L.nsb_info(self.h, out))
         keys = ["n_u", "n_p", "n_cells", "nnz_a00", "nnz_a01", "nnz_a10", "nnz_s", "n_q", "device_bytes", "sweeps_F",
-                "sweeps_S", "schur_mode", "schur_levels"]
+                "sweeps_S", "schur_mode", "schur_levels", "slab_entries", "slab_window_total", "slab_count"]
         return dict(zip(keys, [int(v) for v in out]))
