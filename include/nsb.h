@@ -137,8 +137,9 @@ int nsb_timers(const nsb_ctx *ctx, double out_ms[4]);
  *       [10] fine-level S sweeps per preconditioner application [11] Schur solver mode
  *       [12] number of levels of the Schur hierarchy
  *       [13] entries of the slab storage of F_s incl. padding [14] sum of the slab windows (nodes)
- *       [15] number of slabs */
-int nsb_info(const nsb_ctx *ctx, int64_t out[16]);
+ *       [15] number of slabs [16] entries of the slab storage of A01 incl. padding
+ *       [17] sum of the pressure windows */
+int nsb_info(const nsb_ctx *ctx, int64_t out[18]);
 
 /* Host-only check of the slab (windowed sliced-ELL) storage the solver kernels stream F_s from
  * (csrc/slab.cuh): builds the layout from a node-level CSR pattern and evaluates y = (F_s (x) I_dim) x
@@ -146,6 +147,12 @@ int nsb_info(const nsb_ctx *ctx, int64_t out[16]);
  * stats: [0] slabs [1] stored entries [2] entries incl. padding [3] largest window [4] sum of windows. */
 int nsb_slab_host_check(int dim, int64_t n_rows, int64_t n_cols, const int64_t *rowptr, const uint32_t *colind,
                         const double *val, uint32_t window_cap, const double *x, double *y, int64_t stats[5]);
+
+/* Same for A01 in the slabs of the node pattern: y = A01 xp (n_nodes*dim rows) evaluated on the host in
+ * kernel order.  stats: [0] stored entries [1] entries incl. padding [2] largest pressure window. */
+int nsb_gslab_host_check(int dim, int64_t n_nodes, int64_t n_node_cols, const int64_t *node_rowptr,
+                         const uint32_t *node_colind, uint32_t window_cap, const int64_t *rowptr01,
+                         const uint32_t *colind01, const double *val01, const double *xp, double *y, int64_t stats[3]);
 
 /* pinned host memory for callers that want asynchronous copies */
 void *nsb_alloc_pinned(int64_t bytes);

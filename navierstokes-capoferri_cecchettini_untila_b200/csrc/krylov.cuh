@@ -3,16 +3,16 @@
 // PreconditionASIMPLE::vmult issue one at a time, reference
 // src/NavierStokes.cpp:348, 377, 978-994).
 //
-// Orthogonalisation is classical Gram-Schmidt applied twice (CGS2): one
-// kernel forms all k inner products V^T w reading w and each basis vector
-// once, one kernel applies w -= V h.  All reductions are deterministic: block
-// partials are combined in a fixed order by the last block to finish.
+// Orthogonalisation is classical Gram-Schmidt applied twice (CGS2) in three
+// passes over the basis instead of four: inner products, then projection fused
+// with the second set of inner products, then the second projection fused with
+// the norm (ortho_kernel).  All reductions are deterministic: block partials are
+// combined in a fixed order by the last block to finish.
 #pragma once
 #include "common.cuh"
 
 namespace nsb {
 
-constexpr int kDotChunk = 8;
 constexpr int kRedBlocks = kNumSM * 4;  // grid of every reduction kernel
 constexpr int kRedThreads = 256;
 constexpr int kMaxDots = 64;            // restart length + 2 at most
@@ -45,37 +45,82 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double *smem /* NV
 // single GPU.
 __device__ __forceinline__ int64_t active_index(int64_t e, int64_t n1, int64_t gap) { return e < n1 ? e : e + gap; }
 
-// out[i] = V_i . w for i < k (V_i = V + i*ld); out[k] = w . w when with_self.
-// partials: kMaxDots * gridDim.x doubles; counter: one unsigned, zero on entry
-// and reset to zero on exit.
-__global__ void __launch_bounds__(kRedThreads) multi_dot_kernel(const double *__restrict__ V, int64_t ld, int k,
-                                                                const double *__restrict__ w, int64_t n, int64_t n1,
-                                                                int64_t gap, int with_self,
-                                                                double *__restrict__ out, double *partials,
-                                                                unsigned *counter) {
-  __shared__ double smem[kDotChunk * (kRedThreads / 32)];
+// The three passes of one CGS2 orthogonalisation step, all instances of one kernel:
+//   MODE 0:  out[i] = V_i . w (i < k), out[k] = w . w when with_self
+//   MODE 1:  w += sign * V coef, then out[i] = V_i . w of the UPDATED w -- the basis is read once
+//            for the first projection and the second set of inner products
+//   MODE 2:  w += sign * V coef, then out[0] = w . w when with_self
+// K >= k is the compile-time width (multiple of 4): every thread keeps the K basis entries of an
+// element in registers, so K + 1 independent loads per element are in flight (deep memory-level
+// parallelism is what an HBM-bound reduction over k+1 streams needs), U elements per thread.
+// Updates run over the first n_upd active entries, reductions over the first n_dot (on several
+// GPUs the replicated pressure part is updated everywhere but counted on one rank only).
+// partials: (K+1) * gridDim.x doubles; counter: one unsigned, zero on entry, reset on exit.
+// Reductions are deterministic: block partials are summed in a fixed order by the last block.
+template <int K, int U, int MODE>
+__global__ void __launch_bounds__(kRedThreads)
+    ortho_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ coef, double sign,
+                 double *w, int64_t n_upd, int64_t n_dot, int64_t n1, int64_t gap, int with_self,
+                 double *__restrict__ out, double *partials, unsigned *counter) {
+  __shared__ double s_coef[K];
+  __shared__ double smem[kRedThreads / 32];
   __shared__ bool is_last;
-  const int total = k + (with_self ? 1 : 0);
-  for (int c0 = 0; c0 < total; c0 += kDotChunk) {
-    double acc[kDotChunk];
+  if (MODE != 0) {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s_coef[i] = i < k ? sign * coef[i] : 0.0;
+    __syncthreads();
+  }
+  constexpr int NA = MODE == 2 ? 1 : K;
+  double acc[NA], self = 0.0;
 #pragma unroll
-    for (int j = 0; j < kDotChunk; ++j) acc[j] = 0.0;
-    const int cnt = min(kDotChunk, total - c0);
-    for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t e = active_index(a, n1, gap);
-      const double we = w[e];
+  for (int i = 0; i < NA; ++i) acc[i] = 0.0;
+  const int64_t n = n_upd > n_dot ? n_upd : n_dot;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t0 < n; t0 += U * stride) {
+    double wv[U], v[U][K];
+    int64_t e[U];
 #pragma unroll
-      for (int j = 0; j < kDotChunk; ++j)
-        if (j < cnt) {
-          const int i = c0 + j;
-          acc[j] += (i < k ? V[(int64_t)i * ld + e] : we) * we;
-        }
+    for (int u = 0; u < U; ++u) {
+      const int64_t t = t0 + u * stride;
+      e[u] = active_index(t < n ? t : n - 1, n1, gap);
+      wv[u] = t < n ? w[e[u]] : 0.0;
+#pragma unroll
+      for (int i = 0; i < K; ++i) v[u][i] = (i < k && t < n) ? __ldcs(V + (int64_t)i * ld + e[u]) : 0.0;
     }
-    block_reduce<kDotChunk>(acc, smem);
-    if (threadIdx.x == 0)
 #pragma unroll
-      for (int j = 0; j < kDotChunk; ++j)
-        if (j < cnt) partials[(int64_t)(c0 + j) * gridDim.x + blockIdx.x] = acc[j];
+    for (int u = 0; u < U; ++u) {
+      const int64_t t = t0 + u * stride;
+      double a = wv[u];
+      if (MODE != 0) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) a += s_coef[i] * v[u][i];
+        if (t < n_upd) w[e[u]] = a;
+      }
+      if (t < n_dot) {
+        if (MODE != 2) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) acc[i] += v[u][i] * a;
+        }
+        self += a * a;
+      }
+    }
+  }
+  if (MODE == 2 && !with_self) return;
+  const int total = MODE == 2 ? 1 : k + (with_self ? 1 : 0);
+  // block partials: acc[0..k) then self
+  if (MODE != 2) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      if (i < k) {  // k is uniform
+        double one[1] = {acc[i]};
+        block_reduce<1>(one, smem);
+        if (threadIdx.x == 0) partials[(int64_t)i * gridDim.x + blockIdx.x] = one[0];
+      }
+    }
+  }
+  if (MODE == 2 || with_self) {
+    double one[1] = {self};
+    block_reduce<1>(one, smem);
+    if (threadIdx.x == 0) partials[(int64_t)(MODE == 2 ? 0 : k) * gridDim.x + blockIdx.x] = one[0];
   }
   __threadfence();
   if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
@@ -90,46 +135,6 @@ __global__ void __launch_bounds__(kRedThreads) multi_dot_kernel(const double *__
       if ((threadIdx.x & 31) == 0) out[i] = s;
     }
     if (threadIdx.x == 0) *counter = 0;
-  }
-}
-
-// w += sum_{i<k} sign * coef[i] * V_i ;  optionally out_norm2 = w . w afterwards
-__global__ void __launch_bounds__(kRedThreads) multi_axpy_kernel(const double *__restrict__ V, int64_t ld, int k,
-                                                                 const double *__restrict__ coef, double sign,
-                                                                 double *__restrict__ w, int64_t n, int64_t n1,
-                                                                 int64_t gap, int64_t n_norm, int with_norm,
-                                                                 double *__restrict__ out_norm2, double *partials,
-                                                                 unsigned *counter) {
-  __shared__ double s_coef[kMaxDots];
-  __shared__ double smem[kRedThreads / 32];
-  __shared__ bool is_last;
-  for (int i = threadIdx.x; i < k; i += blockDim.x) s_coef[i] = sign * coef[i];
-  __syncthreads();
-  double nrm[1] = {0.0};
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = active_index(t, n1, gap);
-    double a = w[e];
-#pragma unroll 4
-    for (int i = 0; i < k; ++i) a += s_coef[i] * V[(int64_t)i * ld + e];
-    w[e] = a;
-    if (t < n_norm) nrm[0] += a * a;  // the replicated part is counted on one rank only
-  }
-  if (!with_norm) return;
-  block_reduce<1>(nrm, smem);
-  if (threadIdx.x == 0) partials[blockIdx.x] = nrm[0];
-  __threadfence();
-  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (is_last && threadIdx.x < 32) {
-    __threadfence();
-    double s = 0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) s += partials[b];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) {
-      *out_norm2 = s;
-      *counter = 0;
-    }
   }
 }
 

@@ -68,7 +68,9 @@ struct nsb_ctx {
   double rF = 6.0, rS = 300.0;
   DevBuf<double> mdiag;          // diagonal of the velocity mass matrix (owned nodes)
   SlabDev fslab;                 // F_s in slab (windowed sliced-ELL) form: what the solver kernels stream
-  size_t fslab_smem = 0;         // dynamic shared memory of the slab kernels
+  GSlabDev gslab;                // A01 in the same slabs
+  size_t fslab_smem = 0, fapply_smem = 0, gapply_smem = 0;  // dynamic shared memory of the slab kernels
+  uint32_t fslab_win_doubles = 0;
   DevBuf<double> chzA, chzB;     // Chebyshev iterates on F (ping-pong)
   // The preconditioner application is a fixed sequence of ~100 short launches per outer iteration: it is
   // captured into a CUDA graph once per time step (tmpN -> pz) and replayed (NSB_GRAPH=0 disables).
@@ -153,7 +155,7 @@ inline unsigned blocks_for(int64_t n_threads, int block = 256) { return (unsigne
     NSB_CUDA(cudaGetLastError());                                \
   } while (0)
 
-void fs_apply(nsb_ctx *c, int mode, bool with_a01, const double *xu, const double *xp, const double *d, double *y);
+void fs_apply(nsb_ctx *c, int mode, const double *xu, const double *xp, const double *d, double *y);
 
 // ---- NCCL, resolved at run time so that single-GPU users need no NCCL at all ----
 struct NcclApi {
@@ -260,7 +262,7 @@ void spmv(nsb_ctx *c, const CsrDev &A, int mode, const double *x, const double *
 // y = A x on the compressed storage: velocity rows F_s (+A01), pressure rows A10
 void block_spmv(nsb_ctx *c, const double *x, double *y) {
   halo_exchange(c, const_cast<double *>(x));
-  fs_apply(c, 0, true, x, x + c->n_uloc, nullptr, y);
+  fs_apply(c, 0, x, x + c->n_uloc, nullptr, y);
   spmv(c, c->a10, 0, x, nullptr, nullptr, y + c->n_uloc + c->p_begin);
   allgather_p(c, y + c->n_uloc);
 }
@@ -285,20 +287,31 @@ void cheb_sweep(nsb_ctx *c, const CsrDev &M, const double *dinv, const double *b
   if (L == 32) NSB_LAUNCH(c, cheb_sweep_kernel<32>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
 }
 
-// y_u = F x_u (+ A01 x_p)  [mode 0]  or  y = d .* (F x_u)  [mode 3], on the slab storage of F_s
-void fs_apply(nsb_ctx *c, int mode, bool with_a01, const double *xu, const double *xp, const double *d, double *y) {
-  CsrView a01 = c->a01.view();
-  if (!with_a01) a01.rowptr = nullptr;
+// y_u = F x_u + A01 x_p  [mode 0]  or  y = d .* (F x_u)  [mode 3], on the slab storage of F_s and A01
+void fs_apply(nsb_ctx *c, int mode, const double *xu, const double *xp, const double *d, double *y) {
   const unsigned grid = (unsigned)c->fslab.n_slabs;
   const SlabView S = c->fslab.view();
-#define NSB_FS_CASE(DD, MM)           \
-  if (c->dim == DD && mode == MM)     \
-  NSB_LAUNCH_SMEM(c, (fs_slab_apply_kernel<DD, MM>), grid, kSlabThreads, c->fslab_smem, S, a01, xu, xp, d, y)
+  const GSlabView G = c->gslab.view();
+#define NSB_FS_CASE(DD, MM)                                                                                  \
+  if (c->dim == DD && mode == MM)                                                                            \
+  NSB_LAUNCH_SMEM(c, (fs_slab_apply_kernel<DD, MM>), grid, kSlabThreads, MM == 0 ? c->fapply_smem : c->fslab_smem, S, G, \
+                  c->fslab_win_doubles, xu, xp, d, y)
   NSB_FS_CASE(2, 0);
   NSB_FS_CASE(2, 3);
   NSB_FS_CASE(3, 0);
   NSB_FS_CASE(3, 3);
 #undef NSB_FS_CASE
+}
+
+// y = w - d .* (A01 xp) over the owned velocity rows
+void g_apply(nsb_ctx *c, const double *xp, const double *w, const double *d, double *y) {
+  const unsigned grid = (unsigned)c->fslab.n_slabs;
+  if (c->dim == 2)
+    NSB_LAUNCH_SMEM(c, g_slab_apply_kernel<2>, grid, kSlabThreads, c->gapply_smem, c->fslab.view(), c->gslab.view(), xp,
+                    w, d, y);
+  else
+    NSB_LAUNCH_SMEM(c, g_slab_apply_kernel<3>, grid, kSlabThreads, c->gapply_smem, c->fslab.view(), c->gslab.view(), xp,
+                    w, d, y);
 }
 
 void fs_cheb_sweep(nsb_ctx *c, const double *dinv, const double *b, const double *z, double *d, double *znew, double c1,
@@ -355,22 +368,64 @@ void cheb_solve(nsb_ctx *c, const CsrDev *M, const double *dinv, const double *b
 // dofs; P: a replicated pressure vector (no communication).
 enum class Part { FULL, U, P };
 
+// one launch of ortho_kernel for k <= 32 basis vectors
+template <int MODE>
+void ortho_launch(nsb_ctx *c, const double *V, int64_t ld, int k, const double *coef, double sign, double *w,
+                  int64_t n_upd, int64_t n_dot, int64_t n1, int64_t gap, bool with_self, double *out) {
+#define NSB_ORTHO_CASE(KK, UU)                                                                                       \
+  if (k <= KK) {                                                                                                     \
+    NSB_LAUNCH(c, (ortho_kernel<KK, UU, MODE>), kRedBlocks, kRedThreads, V, ld, k, coef, sign, w, n_upd, n_dot, n1,  \
+               gap, with_self ? 1 : 0, out, c->partials.p, c->counter.p);                                            \
+    return;                                                                                                          \
+  }
+  NSB_ORTHO_CASE(4, 4)
+  NSB_ORTHO_CASE(8, 4)
+  NSB_ORTHO_CASE(12, 2)
+  NSB_ORTHO_CASE(16, 2)
+  NSB_ORTHO_CASE(20, 1)
+  NSB_ORTHO_CASE(24, 1)
+  NSB_ORTHO_CASE(28, 1)
+  NSB_ORTHO_CASE(32, 1)
+#undef NSB_ORTHO_CASE
+  throw ArgError("ortho_launch: more than 32 vectors in one pass");
+}
+constexpr int kOrthoMax = 32;
+
 void multi_dot(nsb_ctx *c, const double *V, int64_t ld, int k, const double *w, Part part, bool with_self,
                double *out, int64_t n_replicated = -1 /* length of a Part::P vector, default n_p */) {
   const int64_t nu = c->n_u, np = n_replicated >= 0 ? n_replicated : (int64_t)c->n_p;
   const int64_t n = part == Part::FULL ? nu + (c->rank == 0 ? np : 0) : part == Part::U ? nu : np;
   const int64_t n1 = part == Part::P ? np : nu, gap = part == Part::FULL ? c->n_uloc - nu : 0;
-  NSB_LAUNCH(c, multi_dot_kernel, kRedBlocks, kRedThreads, V, ld, k, w, n, n1, gap, with_self ? 1 : 0, out,
-             c->partials.p, c->counter.p);
+  for (int k0 = 0; k0 < k || k0 == 0; k0 += kOrthoMax) {  // restart lengths beyond 32: several passes
+    const int kk = std::min(kOrthoMax, k - k0);
+    const bool self = with_self && k0 + kk == k;
+    ortho_launch<0>(c, V + (int64_t)k0 * ld, ld, kk, nullptr, 0.0, const_cast<double *>(w), 0, n, n1, gap, self,
+                    out + k0);
+  }
   if (part != Part::P) allreduce_sum(c, out, (size_t)k + (with_self ? 1 : 0));
 }
 // w += sign * V coef over the FULL part; optionally the squared norm of the result
 void multi_axpy(nsb_ctx *c, const double *V, int64_t ld, int k, const double *coef, double sign, double *w,
                 bool with_norm, double *out_norm2) {
   const int64_t nu = c->n_u, np = c->n_p;
-  NSB_LAUNCH(c, multi_axpy_kernel, kRedBlocks, kRedThreads, V, ld, k, coef, sign, w, nu + np, nu, c->n_uloc - nu,
-             nu + (c->rank == 0 ? np : 0), with_norm ? 1 : 0, out_norm2, c->partials.p, c->counter.p);
+  for (int k0 = 0; k0 < k; k0 += kOrthoMax) {
+    const int kk = std::min(kOrthoMax, k - k0);
+    ortho_launch<2>(c, V + (int64_t)k0 * ld, ld, kk, coef + k0, sign, w, nu + np, nu + (c->rank == 0 ? np : 0), nu,
+                    c->n_uloc - nu, with_norm && k0 + kk == k, out_norm2);
+  }
   if (with_norm) allreduce_sum(c, out_norm2, 1);
+}
+// w += sign * V coef, then out[i] = V_i . w (one read of the basis for both)
+void multi_axpy_dot(nsb_ctx *c, const double *V, int64_t ld, int k, const double *coef, double sign, double *w,
+                    double *out) {
+  if (k > kOrthoMax) {
+    multi_axpy(c, V, ld, k, coef, sign, w, false, nullptr);
+    multi_dot(c, V, ld, k, w, Part::FULL, false, out);
+    return;
+  }
+  const int64_t nu = c->n_u, np = c->n_p;
+  ortho_launch<1>(c, V, ld, k, coef, sign, w, nu + np, nu + (c->rank == 0 ? np : 0), nu, c->n_uloc - nu, false, out);
+  allreduce_sum(c, out, (size_t)k);
 }
 
 double norm2_host(nsb_ctx *c, const double *v, Part part) {
@@ -398,7 +453,7 @@ double power_lmax(nsb_ctx *c, const CsrDev *M /* nullptr: F */, const double *di
       spmv(c, *M, 3, v, nullptr, dinv, w);
     else {
       halo_exchange(c, v);
-      fs_apply(c, 3, false, v, nullptr, dinv, w);
+      fs_apply(c, 3, v, nullptr, dinv, w);
     }
     multi_dot(c, nullptr, 0, 0, w, part, true, h, n);
     NSB_LAUNCH(c, normalize_kernel, kRedBlocks, 256, n, h, w, v);
@@ -497,17 +552,31 @@ void build_fslab(nsb_ctx *c) {
   if (const char *e = std::getenv("NSB_SLAB_WINDOW")) cap = (uint32_t)std::max(64, std::atoi(e));
   const SlabHost H = build_slabs(F.n_rows, c->n_uloc / c->dim, rp.data(), ci.data(), cap);
   upload_slabs(H, F.n_rows, c->fslab, c->stream, &c->dev_bytes);
-  c->fslab_smem = sizeof(double) * c->dim * std::max<size_t>(c->fslab.max_window, kSlabThreads);
-  auto prep = [&](const void *f) {
-    NSB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fslab_smem));
+  {
+    const CsrDev &B = c->a01;
+    std::vector<int64_t> rp01((size_t)B.n_rows + 1);
+    std::vector<uint32_t> ci01((size_t)B.nnz);
+    B.rowptr.download(rp01.data(), c->stream);
+    B.colind.download(ci01.data(), c->stream);
+    const GSlabHost G = build_gslabs(c->dim, H.slab_row, rp01.data(), ci01.data());
+    upload_gslabs(G, c->gslab, c->stream, &c->dev_bytes);
+  }
+  c->fslab_win_doubles = (uint32_t)(c->dim * std::max<size_t>(c->fslab.max_window, kSlabThreads));
+  c->fslab_smem = sizeof(double) * c->fslab_win_doubles;
+  c->gapply_smem = sizeof(double) * ((size_t)c->dim * kSlabThreads + c->gslab.max_window);
+  c->fapply_smem = c->fslab_smem + c->gapply_smem;
+  auto prep = [&](const void *f, size_t smem) {
+    NSB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NSB_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   };
-  prep((const void *)fs_slab_apply_kernel<2, 0>);
-  prep((const void *)fs_slab_apply_kernel<2, 3>);
-  prep((const void *)fs_slab_apply_kernel<3, 0>);
-  prep((const void *)fs_slab_apply_kernel<3, 3>);
-  prep((const void *)fs_slab_sweep_kernel<2>);
-  prep((const void *)fs_slab_sweep_kernel<3>);
+  prep((const void *)fs_slab_apply_kernel<2, 0>, c->fapply_smem);
+  prep((const void *)fs_slab_apply_kernel<2, 3>, c->fslab_smem);
+  prep((const void *)fs_slab_apply_kernel<3, 0>, c->fapply_smem);
+  prep((const void *)fs_slab_apply_kernel<3, 3>, c->fslab_smem);
+  prep((const void *)fs_slab_sweep_kernel<2>, c->fslab_smem);
+  prep((const void *)fs_slab_sweep_kernel<3>, c->fslab_smem);
+  prep((const void *)g_slab_apply_kernel<2>, c->gapply_smem);
+  prep((const void *)g_slab_apply_kernel<3>, c->gapply_smem);
 }
 
 void finalize_setup(nsb_ctx *c) {
@@ -660,6 +729,8 @@ void assemble_launch(nsb_ctx *c) {
   // the solver streams F_s in slab order
   NSB_LAUNCH(c, slab_repack_kernel, blocks_for(c->fslab.padded), 256, c->fslab.padded, c->fslab.src.p, c->fs.val.p,
              c->fslab.val.p);
+  NSB_LAUNCH(c, slab_repack_kernel, blocks_for(c->gslab.padded), 256, c->gslab.padded, c->gslab.src.p, c->a01.val.p,
+             c->gslab.val.p);
 }
 
 // ---- preconditioner -------------------------------------------------------
@@ -861,7 +932,7 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
   }
   NSB_LAUNCH(c, scale_kernel, blocks_for(np), 256, np, -1.0 / c->alpha, d1, dst + c->n_uloc);
   // dst0 = vec0 - Di .* (Bt dst1)                        (:992-994)
-  spmv(c, c->a01, 2, dst + c->n_uloc, c->vec0.p, c->di.p, dst);
+  g_apply(c, dst + c->n_uloc, c->vec0.p, c->di.p, dst);
 }
 
 // pz = P^-1 tmpN, as a CUDA graph captured once per time step (the coefficients of the sweeps change with
@@ -958,8 +1029,7 @@ int gmres_solve(nsb_ctx *c, double tol) {
       dim = j + 1;
       // CGS2: h = V^T vv; vv -= V h; h2 = V^T vv; vv -= V h2; s = ||vv||
       multi_dot(c, V, N, dim, vv, Part::FULL, false, hd);
-      multi_axpy(c, V, N, dim, hd, -1.0, vv, false, nullptr);
-      multi_dot(c, V, N, dim, vv, Part::FULL, false, hd + kMaxDots);
+      multi_axpy_dot(c, V, N, dim, hd, -1.0, vv, hd + kMaxDots);
       multi_axpy(c, V, N, dim, hd + kMaxDots, -1.0, vv, true, hd + 2 * kMaxDots);
       NSB_CUDA(cudaMemcpyAsync(h.data(), hd, sizeof(double) * dim, cudaMemcpyDeviceToHost, c->stream));
       NSB_CUDA(cudaMemcpyAsync(h2.data(), hd + kMaxDots, sizeof(double) * dim, cudaMemcpyDeviceToHost, c->stream));
@@ -1505,7 +1575,7 @@ int nsb_timers(const nsb_ctx *c, double out_ms[4]) {
   for (int i = 0; i < 4; ++i) out_ms[i] = c->t_ms[i];
   return NSB_OK;
 }
-int nsb_info(const nsb_ctx *c, int64_t out[16]) {
+int nsb_info(const nsb_ctx *c, int64_t out[18]) {
   if (!c) return NSB_EARG;
   out[0] = c->n_u;
   out[1] = c->n_p;
@@ -1523,6 +1593,8 @@ int nsb_info(const nsb_ctx *c, int64_t out[16]) {
   out[13] = c->fslab.padded;
   out[14] = (int64_t)c->fslab.win_list.n;
   out[15] = c->fslab.n_slabs;
+  out[16] = c->gslab.padded;
+  out[17] = (int64_t)c->gslab.pwin_list.n;
   return NSB_OK;
 }
 
@@ -1564,6 +1636,41 @@ int nsb_slab_host_check(int dim, int64_t n_rows, int64_t n_cols, const int64_t *
     stats[2] = H.slice_ptr.back();
     stats[3] = H.max_window;
     stats[4] = (int64_t)H.win_list.size();
+    return NSB_OK;
+  } catch (const StructError &) {
+    return NSB_ESTRUCT;
+  } catch (...) {
+    return NSB_EARG;
+  }
+}
+
+int nsb_gslab_host_check(int dim, int64_t n_nodes, int64_t n_node_cols, const int64_t *node_rowptr,
+                         const uint32_t *node_colind, uint32_t window_cap, const int64_t *rowptr01,
+                         const uint32_t *colind01, const double *val01, const double *xp, double *y, int64_t stats[3]) {
+  try {
+    if ((dim != 2 && dim != 3) || !node_rowptr || !node_colind || !rowptr01 || !colind01 || !val01 || !xp || !y || !stats)
+      return NSB_EARG;
+    const SlabHost H = build_slabs(n_nodes, n_node_cols, node_rowptr, node_colind, window_cap);
+    const GSlabHost G = build_gslabs(dim, H.slab_row, rowptr01, colind01);
+    const int64_t ns = (int64_t)H.slab_row.size() - 1;
+    for (int64_t s = 0; s < ns; ++s) {  // what slab_g_product does
+      const uint32_t w0 = G.pwin_ptr[s];
+      const int64_t d0 = (int64_t)dim * H.slab_row[s], nd = (int64_t)dim * (H.slab_row[s + 1] - H.slab_row[s]);
+      for (int64_t i = 0; i < nd; ++i) {
+        const int64_t sl = s * kGSlices + i / 32, base = G.slice_ptr[sl] + i % 32;
+        const int W = (int)((G.slice_ptr[sl + 1] - G.slice_ptr[sl]) >> 5);
+        double a0 = 0.0;
+        for (int k = 0; k < W; ++k) {
+          const int64_t p = base + 32 * (int64_t)k;
+          const double v = G.src[p] != kSlabPad ? val01[G.src[p]] : 0.0;
+          a0 += v * xp[G.pwin_list[w0 + G.idx[p]]];
+        }
+        y[d0 + G.perm[(size_t)(d0 + i)]] = a0;
+      }
+    }
+    stats[0] = G.nnz;
+    stats[1] = G.slice_ptr.back();
+    stats[2] = G.max_window;
     return NSB_OK;
   } catch (const StructError &) {
     return NSB_ESTRUCT;

@@ -256,31 +256,6 @@ __device__ __forceinline__ double slab_row_sum(const double *sm, uint32_t vp, in
   return s;
 }
 
-// velocity rows of the block product:  y_u = F x_u (+ A01 x_p when a01.rowptr)
-//   MODE 0: y = ..., MODE 3: y = d .* (F x)   (power iteration on D^-1 F)
-template <int DIM, int MODE>
-__global__ void __launch_bounds__(kSlabThreads) fs_slab_apply_kernel(SlabView S, CsrView a01,
-                                                                     const double *__restrict__ xu,
-                                                                     const double *__restrict__ xp,
-                                                                     const double *__restrict__ d,
-                                                                     double *__restrict__ y) {
-  extern __shared__ double sm[];
-  const int s = blockIdx.x;
-  double acc[DIM];
-  slab_product<DIM>(S, s, xu, sm, acc);
-  const uint32_t r0 = S.slab_row[s], nr = S.slab_row[s + 1] - r0;
-  for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
-    const uint32_t r = i / DIM;
-    double sc = slab_row_sum<DIM>(sm, S.vpos[r0 + r], (int)(i % DIM));
-    const int64_t g = (int64_t)DIM * r0 + i;
-    if (MODE == 0 && a01.rowptr != nullptr) {
-      const int64_t b = a01.rowptr[g], e = a01.rowptr[g + 1];
-      for (int64_t k = b; k < e; ++k) sc += __ldcs(a01.val + k) * __ldg(xp + __ldcs(a01.colind + k));
-    }
-    y[g] = MODE == 3 ? d[g] * sc : sc;
-  }
-}
-
 // One Chebyshev-Jacobi sweep on F z = b (see cheb_sweep_kernel in spmv.cuh):
 //   dnew = c1 * d + c2 * Dinv .* (b - F z);  znew = z + dnew      (z, znew distinct)
 template <int DIM>
@@ -300,6 +275,195 @@ __global__ void __launch_bounds__(kSlabThreads) fs_slab_sweep_kernel(SlabView S,
     const double dn = c1 * d[g] + c2 * dinv[g] * (b[g] - sc);
     d[g] = dn;
     znew[g] = __ldg(z + g) + dn;
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// A01 (velocity rows x pressure columns, reference system_matrix.block(0,1)) in
+// the same slabs.  The dof rows [dim*r0, dim*r1) of a slab are sorted by length
+// (a vertex node couples to ~15 pressure vertices, an edge node to ~7) and
+// stored as ELL slices of 32 rows with a 16-bit index into the slab's PRESSURE
+// window, which is staged in shared memory like the velocity window.  `perm`
+// maps the sorted position back to the natural dof of the slab so that results
+// are handed over through shared memory and written coalesced.
+// ---------------------------------------------------------------------------
+constexpr int kGSlices = 3 * kSlabThreads / 32;  // dof rows of one slab / 32, at most (dim <= 3)
+
+struct GSlabView {
+  const uint32_t *pwin_ptr;   // n_slabs+1
+  const uint32_t *pwin_list;  // pressure columns, ascending inside a slab
+  const int64_t *slice_ptr;   // n_slabs*kGSlices+1
+  const double *val;
+  const uint16_t *idx;
+  const uint16_t *perm;       // per dof row (slab-major, sorted position) -> natural local dof of the slab
+};
+
+struct GSlabHost {
+  std::vector<uint32_t> pwin_ptr, pwin_list, src;
+  std::vector<int64_t> slice_ptr;
+  std::vector<uint16_t> idx, perm;
+  uint32_t max_window = 0;
+  int64_t nnz = 0;
+};
+
+struct GSlabDev {
+  int64_t nnz = 0, padded = 0;
+  uint32_t max_window = 0;
+  DevBuf<uint32_t> pwin_ptr, pwin_list, src;
+  DevBuf<int64_t> slice_ptr;
+  DevBuf<double> val;
+  DevBuf<uint16_t> idx, perm;
+  bool have = false;
+  GSlabView view() const { return {pwin_ptr.p, pwin_list.p, slice_ptr.p, val.p, idx.p, perm.p}; }
+};
+
+// rp/ci: CSR pattern of A01 (one row per velocity dof, dim rows per node, in node order)
+inline GSlabHost build_gslabs(int dim, const std::vector<uint32_t> &slab_row, const int64_t *rp, const uint32_t *ci) {
+  GSlabHost H;
+  const int64_t ns = (int64_t)slab_row.size() - 1;
+  const int64_t n_rows = (int64_t)dim * slab_row.back();
+  H.nnz = rp[n_rows];
+  if (H.nnz >= (int64_t)kSlabPad) throw ArgError("slab storage: more than 2^32-2 stored entries per rank");
+  std::vector<std::vector<uint32_t>> wins((size_t)ns);
+  std::vector<int64_t> slice_len((size_t)ns * kGSlices, 0);
+  H.perm.assign((size_t)n_rows, 0);
+  uint32_t maxw = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : maxw)
+  for (int64_t s = 0; s < ns; ++s) {
+    const int64_t d0 = (int64_t)dim * slab_row[s], nd = (int64_t)dim * (slab_row[s + 1] - slab_row[s]);
+    std::vector<uint32_t> &w = wins[s];
+    w.assign(ci + rp[d0], ci + rp[d0 + nd]);
+    std::sort(w.begin(), w.end());
+    w.erase(std::unique(w.begin(), w.end()), w.end());
+    if (w.size() > 65535) throw StructError("slab storage: pressure window exceeds 16-bit indices");
+    maxw = std::max(maxw, (uint32_t)w.size());
+    std::vector<uint16_t> order((size_t)nd);
+    for (int64_t i = 0; i < nd; ++i) order[i] = (uint16_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint16_t a, uint16_t b) {
+      return rp[d0 + a + 1] - rp[d0 + a] > rp[d0 + b + 1] - rp[d0 + b];
+    });
+    for (int64_t i = 0; i < nd; ++i) H.perm[(size_t)(d0 + i)] = order[i];
+    for (int64_t wv = 0; wv * 32 < nd; ++wv) {
+      const int64_t r = d0 + order[wv * 32];
+      slice_len[s * kGSlices + wv] = 32 * (rp[r + 1] - rp[r]);
+    }
+  }
+  H.max_window = maxw;
+  H.pwin_ptr.assign((size_t)ns + 1, 0);
+  for (int64_t s = 0; s < ns; ++s) H.pwin_ptr[s + 1] = H.pwin_ptr[s] + (uint32_t)wins[s].size();
+  H.pwin_list.resize(H.pwin_ptr.back());
+  H.slice_ptr.assign((size_t)ns * kGSlices + 1, 0);
+  for (size_t i = 0; i < slice_len.size(); ++i) H.slice_ptr[i + 1] = H.slice_ptr[i] + slice_len[i];
+  H.idx.assign((size_t)H.slice_ptr.back(), 0);
+  H.src.assign((size_t)H.slice_ptr.back(), kSlabPad);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t s = 0; s < ns; ++s) {
+    const std::vector<uint32_t> &w = wins[s];
+    std::copy(w.begin(), w.end(), H.pwin_list.begin() + H.pwin_ptr[s]);
+    const int64_t d0 = (int64_t)dim * slab_row[s], nd = (int64_t)dim * (slab_row[s + 1] - slab_row[s]);
+    for (int64_t i = 0; i < nd; ++i) {
+      const int64_t r = d0 + H.perm[(size_t)(d0 + i)];
+      const int64_t base = H.slice_ptr[s * kGSlices + i / 32] + i % 32;
+      for (int64_t k = rp[r]; k < rp[r + 1]; ++k) {
+        const int64_t p = base + 32 * (k - rp[r]);
+        H.idx[(size_t)p] = (uint16_t)(std::lower_bound(w.begin(), w.end(), ci[k]) - w.begin());
+        H.src[(size_t)p] = (uint32_t)k;
+      }
+    }
+  }
+  return H;
+}
+
+inline void upload_gslabs(const GSlabHost &H, GSlabDev &D, cudaStream_t s, int64_t *bytes) {
+  D.nnz = H.nnz;
+  D.padded = H.slice_ptr.back();
+  D.max_window = H.max_window;
+  D.pwin_ptr.upload(H.pwin_ptr.data(), H.pwin_ptr.size(), s, bytes);
+  D.pwin_list.upload(H.pwin_list.data(), H.pwin_list.size(), s, bytes);
+  D.src.upload(H.src.data(), H.src.size(), s, bytes);
+  D.slice_ptr.upload(H.slice_ptr.data(), H.slice_ptr.size(), s, bytes);
+  D.idx.upload(H.idx.data(), H.idx.size(), s, bytes);
+  D.perm.upload(H.perm.data(), H.perm.size(), s, bytes);
+  D.val.alloc((size_t)D.padded, bytes);
+  D.val.zero(s);
+  NSB_CUDA(cudaStreamSynchronize(s));
+  D.have = true;
+}
+
+// smo[natural local dof] = (A01 xp)[dof] for the dof rows of slab s.  smp: pressure window, smo: dim*nr doubles.
+// Ends with a __syncthreads().
+template <int DIM>
+__device__ __forceinline__ void slab_g_product(const GSlabView &G, int s, uint32_t r0, uint32_t nr,
+                                               const double *__restrict__ xp, double *smp, double *smo) {
+  const int t = threadIdx.x;
+  const uint32_t w0 = G.pwin_ptr[s], nw = G.pwin_ptr[s + 1] - w0;
+  for (uint32_t i = t; i < nw; i += kSlabThreads) smp[i] = __ldg(xp + __ldg(G.pwin_list + w0 + i));
+  __syncthreads();
+  const uint32_t nd = DIM * nr;
+  for (uint32_t i = t; i < nd; i += kSlabThreads) {  // i >> 5 is warp-uniform
+    const int64_t sl = (int64_t)s * kGSlices + (i >> 5);
+    const int64_t base = G.slice_ptr[sl];
+    const int W = (int)((G.slice_ptr[sl + 1] - base) >> 5);
+    const double *__restrict__ v = G.val + base + (t & 31);
+    const uint16_t *__restrict__ ix = G.idx + base + (t & 31);
+    double a0 = 0.0, a1 = 0.0;
+    int k = 0;
+    for (; k + 4 <= W; k += 4) {
+      const double v0 = __ldcs(v + 32 * k), v1 = __ldcs(v + 32 * (k + 1)), v2 = __ldcs(v + 32 * (k + 2)),
+                   v3 = __ldcs(v + 32 * (k + 3));
+      const unsigned j0 = __ldcs(ix + 32 * k), j1 = __ldcs(ix + 32 * (k + 1)), j2 = __ldcs(ix + 32 * (k + 2)),
+                     j3 = __ldcs(ix + 32 * (k + 3));
+      a0 += v0 * smp[j0];
+      a1 += v1 * smp[j1];
+      a0 += v2 * smp[j2];
+      a1 += v3 * smp[j3];
+    }
+    for (; k < W; ++k) a0 += __ldcs(v + 32 * k) * smp[__ldcs(ix + 32 * k)];
+    smo[__ldg(G.perm + (size_t)DIM * r0 + i)] = a0 + a1;
+  }
+  __syncthreads();
+}
+
+// velocity rows of the block product:
+//   MODE 0: y_u = F x_u + A01 x_p     MODE 3: y = d .* (F x)   (power iteration on D^-1 F; G unused)
+// shared memory: [velocity window / partial sums][dim*256 A01 results][pressure window]
+template <int DIM, int MODE>
+__global__ void __launch_bounds__(kSlabThreads) fs_slab_apply_kernel(SlabView S, GSlabView G, uint32_t win_doubles,
+                                                                     const double *__restrict__ xu,
+                                                                     const double *__restrict__ xp,
+                                                                     const double *__restrict__ d,
+                                                                     double *__restrict__ y) {
+  extern __shared__ double sm[];
+  const int s = blockIdx.x;
+  const uint32_t r0 = S.slab_row[s], nr = S.slab_row[s + 1] - r0;
+  double *smo = sm + win_doubles, *smp = smo + DIM * kSlabThreads;
+  if (MODE == 0) slab_g_product<DIM>(G, s, r0, nr, xp, smp, smo);
+  double acc[DIM];
+  slab_product<DIM>(S, s, xu, sm, acc);
+  for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
+    double sc = slab_row_sum<DIM>(sm, S.vpos[r0 + i / DIM], (int)(i % DIM));
+    const int64_t g = (int64_t)DIM * r0 + i;
+    if (MODE == 0) sc += smo[i];
+    y[g] = MODE == 3 ? d[g] * sc : sc;
+  }
+}
+
+// y = w - d .* (A01 xp)   (dst0 = vec0 - Di .* (Bt dst1), reference :992-994) over the velocity rows
+template <int DIM>
+__global__ void __launch_bounds__(kSlabThreads) g_slab_apply_kernel(SlabView S, GSlabView G,
+                                                                    const double *__restrict__ xp,
+                                                                    const double *__restrict__ w,
+                                                                    const double *__restrict__ d,
+                                                                    double *__restrict__ y) {
+  extern __shared__ double sm[];
+  const int s = blockIdx.x;
+  const uint32_t r0 = S.slab_row[s], nr = S.slab_row[s + 1] - r0;
+  double *smo = sm, *smp = sm + DIM * kSlabThreads;
+  slab_g_product<DIM>(G, s, r0, nr, xp, smp, smo);
+  for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
+    const int64_t g = (int64_t)DIM * r0 + i;
+    y[g] = w[g] - d[g] * smo[i];
   }
 }
 

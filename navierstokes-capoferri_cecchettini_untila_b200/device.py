@@ -22,7 +22,7 @@ SYMBOLS = [
     "nsb_compute_forces", "nsb_get_matrix_values", "nsb_get_pattern", "nsb_nnz", "nsb_get_rhs", "nsb_vmult",
     "nsb_bench_kernel", "nsb_launch_count", "nsb_timers", "nsb_info", "nsb_alloc_pinned", "nsb_free_pinned",
     "nsb_comm_unique_id", "nsb_comm_init", "nsb_set_local_dofs", "nsb_set_halo", "nsb_set_schur_solver", "nsb_gather_velocity",
-    "nsb_slab_host_check",
+    "nsb_slab_host_check", "nsb_gslab_host_check",
 ]
 
 
@@ -83,6 +83,8 @@ def device_lib():
         L.nsb_set_halo.argtypes = [p, C.c_int, i32p, i64p, u32p, i64p]
         L.nsb_gather_velocity.argtypes = [p, u32p, f64p]
         L.nsb_slab_host_check.argtypes = [C.c_int, C.c_int64, C.c_int64, i64p, u32p, f64p, C.c_uint32, f64p, f64p, i64p]
+        L.nsb_gslab_host_check.argtypes = [C.c_int, C.c_int64, C.c_int64, i64p, u32p, C.c_uint32, i64p, u32p, f64p, f64p,
+                                           f64p, i64p]
         _lib = L
     return _lib
 
@@ -108,6 +110,26 @@ def slab_host_check(dim, rowptr, colind, val, x, n_cols=None, window_cap=1408):
     if rc != 0:
         raise DeviceError(f"nsb_slab_host_check failed ({rc})")
     return y, dict(zip(["slabs", "nnz", "padded", "max_window", "window_total"], [int(v) for v in st]))
+
+
+def gslab_host_check(dim, node_rowptr, node_colind, rowptr01, colind01, val01, xp, window_cap=1408):
+    """Host evaluation of y = A01 xp through the slab layout of A01 (no device needed)."""
+    node_rowptr = np.ascontiguousarray(node_rowptr, np.int64)
+    node_colind = np.ascontiguousarray(node_colind, np.uint32)
+    rowptr01 = np.ascontiguousarray(rowptr01, np.int64)
+    colind01 = np.ascontiguousarray(colind01, np.uint32)
+    val01 = np.ascontiguousarray(val01, np.float64)
+    xp = np.ascontiguousarray(xp, np.float64)
+    n = node_rowptr.size - 1
+    y = np.zeros(dim * n)
+    st = np.zeros(3, np.int64)
+    rc = device_lib().nsb_gslab_host_check(dim, n, n, _p(node_rowptr, C.c_int64), _p(node_colind, C.c_uint32),
+                                           window_cap, _p(rowptr01, C.c_int64), _p(colind01, C.c_uint32),
+                                           _p(val01, C.c_double), _p(xp, C.c_double), _p(y, C.c_double),
+                                           _p(st, C.c_int64))
+    if rc != 0:
+        raise DeviceError(f"nsb_gslab_host_check failed ({rc})")
+    return y, dict(zip(["nnz", "padded", "max_window"], [int(v) for v in st]))
 
 
 class Device:
@@ -303,8 +325,9 @@ class Device:
         return out
 
     def info(self):
-        out = (C.c_int64 * 16)()
+        out = (C.c_int64 * 18)()
         self._chk(self.L.nsb_info(self.h, out))
         keys = ["n_u", "n_p", "n_cells", "nnz_a00", "nnz_a01", "nnz_a10", "nnz_s", "n_q", "device_bytes", "sweeps_F",
-                "sweeps_S", "schur_mode", "schur_levels", "slab_entries", "slab_window_total", "slab_count"]
+                "sweeps_S", "schur_mode", "schur_levels", "slab_entries", "slab_window_total", "slab_count",
+                "gslab_entries", "gslab_window_total"]
         return dict(zip(keys, [int(v) for v in out]))

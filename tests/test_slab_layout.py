@@ -52,3 +52,22 @@ def test_slab_rectangular_pattern_with_ghost_columns(pkg):
     F = sp.csr_matrix((val, ci2.astype(np.int64), rp2), shape=(n_own, n))
     ref = (F @ x.reshape(n, 3)).ravel()
     assert np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("name,h,dim", [("2d-cylinder", 0.05, 2), ("3d-cylinder", 0.08, 3)])
+@pytest.mark.parametrize("cap", [1408, 120])
+def test_a01_slab_product_matches_csr(pkg, name, h, dim, cap):
+    prob = pkg.Problem.generate(name, h).build(expand_a00=False)
+    rp, ci = prob.array("nodes.rowptr"), prob.array("nodes.colind")
+    rp01, ci01 = prob.array("a01.rowptr"), prob.array("a01.colind")
+    n, n_p = rp.size - 1, prob.sizes()["n_p"]
+    rng = np.random.default_rng(11)
+    val = rng.standard_normal(ci01.size)
+    xp = rng.standard_normal(n_p)
+    y, st = pkg.device.gslab_host_check(dim, rp, ci, rp01, ci01, val, xp, window_cap=cap)
+    B = sp.csr_matrix((val, ci01.astype(np.int64), rp01), shape=(dim * n, n_p))
+    ref = B @ xp
+    assert np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
+    assert st["nnz"] == ci01.size and st["padded"] % 32 == 0
+    if cap == 1408:
+        assert st["padded"] <= 1.25 * st["nnz"], st
