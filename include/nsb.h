@@ -144,9 +144,10 @@ int nsb_info(const nsb_ctx *ctx, int64_t out[18]);
 /* Host-only check of the slab (windowed sliced-ELL) storage the solver kernels stream F_s from
  * (csrc/slab.cuh): builds the layout from a node-level CSR pattern and evaluates y = (F_s (x) I_dim) x
  * on the host in exactly the order the device kernels use.  No device is touched.
- * stats: [0] slabs [1] stored entries [2] entries incl. padding [3] largest window [4] sum of windows. */
+ * stats: [0] slabs [1] stored entries [2] entries incl. padding [3] largest window [4] sum of windows
+ *        [5] 1000 x shared-memory wavefronts per half-warp gather (1000 = free of bank conflicts). */
 int nsb_slab_host_check(int dim, int64_t n_rows, int64_t n_cols, const int64_t *rowptr, const uint32_t *colind,
-                        const double *val, uint32_t window_cap, const double *x, double *y, int64_t stats[5]);
+                        const double *val, uint32_t window_cap, const double *x, double *y, int64_t stats[6]);
 
 /* Same for A01 in the slabs of the node pattern: y = A01 xp (n_nodes*dim rows) evaluated on the host in
  * kernel order.  stats: [0] stored entries [1] entries incl. padding [2] largest pressure window. */

@@ -548,8 +548,7 @@ void build_fslab(nsb_ctx *c) {
   std::vector<uint32_t> ci((size_t)F.nnz);
   F.rowptr.download(rp.data(), c->stream);
   F.colind.download(ci.data(), c->stream);
-  uint32_t cap = c->dim == 3 ? 1408u : 2112u;
-  if (const char *e = std::getenv("NSB_SLAB_WINDOW")) cap = (uint32_t)std::max(64, std::atoi(e));
+  const uint32_t cap = c->dim == 3 ? 1408u : 2112u;
   const SlabHost H = build_slabs(F.n_rows, c->n_uloc / c->dim, rp.data(), ci.data(), cap);
   upload_slabs(H, F.n_rows, c->fslab, c->stream, &c->dev_bytes);
   {
@@ -1599,7 +1598,7 @@ int nsb_info(const nsb_ctx *c, int64_t out[18]) {
 }
 
 int nsb_slab_host_check(int dim, int64_t n_rows, int64_t n_cols, const int64_t *rowptr, const uint32_t *colind,
-                        const double *val, uint32_t window_cap, const double *x, double *y, int64_t stats[5]) {
+                        const double *val, uint32_t window_cap, const double *x, double *y, int64_t stats[6]) {
   try {
     if ((dim != 2 && dim != 3) || !rowptr || !colind || !val || !x || !y || !stats) return NSB_EARG;
     const SlabHost H = build_slabs(n_rows, n_cols, rowptr, colind, window_cap);
@@ -1615,7 +1614,7 @@ int nsb_slab_host_check(int dim, int64_t n_rows, int64_t n_cols, const int64_t *
         const int W = (int)((H.slice_ptr[sl + 1] - base) >> 5);
         for (int c = 0; c < dim; ++c) part[(size_t)t * dim + c] = 0.0;
         for (int k = 0; k < W; ++k) {
-          const int64_t p = base + 32 * (int64_t)k + (t & 31);
+          const int64_t p = base + slab_entry_pos(k, t & 31);
           const double a = H.src[p] != kSlabPad ? val[H.src[p]] : 0.0;
           if (H.idx[p] >= std::max<uint32_t>(nw, 1)) return NSB_ESTRUCT;
           for (int c = 0; c < dim; ++c) part[(size_t)t * dim + c] += a * win[(size_t)dim * H.idx[p] + c];
@@ -1636,6 +1635,7 @@ int nsb_slab_host_check(int dim, int64_t n_rows, int64_t n_cols, const int64_t *
     stats[2] = H.slice_ptr.back();
     stats[3] = H.max_window;
     stats[4] = (int64_t)H.win_list.size();
+    stats[5] = (int64_t)std::llround(1000.0 * H.bank_wavefronts_per_step);
     return NSB_OK;
   } catch (const StructError &) {
     return NSB_ESTRUCT;

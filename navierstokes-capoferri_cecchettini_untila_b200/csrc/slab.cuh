@@ -52,12 +52,19 @@ struct SlabView {
   const uint32_t *vpos;      // per real row: 3 x 10-bit thread positions of its chunks (kVposNone = unused)
 };
 
+// Position of entry k of lane `lane` inside a slice: two consecutive entries of a lane are adjacent, so
+// a lane fetches 2 values with one 128-bit load and 2 indices with one 32-bit load (512 B + 128 B per
+// warp request instead of 256 B + 64 B: measured on B200, the matrix stream is limited by the number
+// of requests in flight, not by their bytes).  Slice widths are even.
+__host__ __device__ inline int64_t slab_entry_pos(int k, int lane) { return (int64_t)(k >> 1) * 64 + lane * 2 + (k & 1); }
+
 struct SlabHost {
   std::vector<uint32_t> slab_row, win_ptr, win_list, vpos, src;
   std::vector<int64_t> slice_ptr;
   std::vector<uint16_t> idx;
   uint32_t max_window = 0;
   int64_t nnz = 0;
+  double bank_wavefronts_per_step = 1.0;  // shared-memory wavefronts per half-warp load (1 = conflict-free)
 };
 
 struct SlabDev {
@@ -142,7 +149,7 @@ inline SlabHost build_slabs(int64_t n_rows, int64_t n_cols, const int64_t *rp, c
     }
     std::stable_sort(v.begin(), v.end(), [](const VRow &a, const VRow &b) { return a.len > b.len; });
     for (int w = 0; w < kSlabSlices; ++w)
-      slice_len[s * kSlabSlices + w] = (size_t)w * 32 < v.size() ? 32 * (int64_t)v[(size_t)w * 32].len : 0;
+      slice_len[s * kSlabSlices + w] = (size_t)w * 32 < v.size() ? 32 * (int64_t)((v[(size_t)w * 32].len + 1) & ~1) : 0;
   }
   H.slice_ptr.assign((size_t)ns * kSlabSlices + 1, 0);
   for (size_t i = 0; i < slice_len.size(); ++i) H.slice_ptr[i + 1] = H.slice_ptr[i] + slice_len[i];
@@ -150,25 +157,113 @@ inline SlabHost build_slabs(int64_t n_rows, int64_t n_cols, const int64_t *rp, c
   H.idx.assign((size_t)total, 0);
   H.src.assign((size_t)total, kSlabPad);
   H.vpos.assign((size_t)n_rows, kVposNone | (kVposNone << 10) | (kVposNone << 20));
+  // pass 3 (parallel): fill.  The order of the entries inside a virtual row is free, so it is chosen
+  // per half-warp (the unit in which a 64-bit shared-memory load is served) such that at every step
+  // the 16 lanes read window nodes with distinct (index mod 16), i.e. distinct bank pairs for each of
+  // the dim components: a lane takes a free residue when it has one, idles (zero padding) when it has
+  // slack in its slice, and only otherwise accepts a bank conflict.  ncu before this ordering: 2.2
+  // conflict wavefronts per shared load, L1/shared pipe the busiest unit of the sweep kernel at 73 %.
   uint32_t maxw = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(max : maxw)
+  int64_t wavefronts = 0, steps = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : maxw) reduction(+ : wavefronts, steps)
   for (int64_t s = 0; s < ns; ++s) {
     const uint32_t *wb = H.win_list.data() + H.win_ptr[s], *we = H.win_list.data() + H.win_ptr[s + 1];
-    maxw = std::max(maxw, (uint32_t)(we - wb));
+    const uint32_t nw = (uint32_t)(we - wb);
+    maxw = std::max(maxw, nw);
     const std::vector<VRow> &v = vrows[s];
     for (size_t t = 0; t < v.size(); ++t) {
-      const VRow &q = v[t];
-      const int64_t base = H.slice_ptr[s * kSlabSlices + (int64_t)(t >> 5)] + (int64_t)(t & 31);
-      for (int k = 0; k < q.len; ++k) {
-        const int64_t p = rp[q.row] + q.off + k;
-        H.idx[(size_t)(base + 32 * (int64_t)k)] = (uint16_t)(std::lower_bound(wb, we, ci[p]) - wb);
-        H.src[(size_t)(base + 32 * (int64_t)k)] = (uint32_t)p;
+      uint32_t &vp = H.vpos[v[t].row];  // the chunks of a row live in one slab: no race across threads
+      vp = (vp & ~(0x3ffu << (10 * v[t].chunk))) | ((uint32_t)t << (10 * v[t].chunk));
+    }
+    struct Ent {
+      uint16_t idx;
+      uint32_t src;
+    };
+    std::vector<Ent> ent[16];
+    for (size_t h0 = 0; h0 < v.size(); h0 += 16) {  // one half-warp
+      const int64_t sl = s * kSlabSlices + (int64_t)(h0 >> 5);
+      const int W = (int)((H.slice_ptr[sl + 1] - H.slice_ptr[sl]) >> 5);
+      const int nl = (int)std::min<size_t>(16, v.size() - h0);
+      int cnt[16][16], rem[16], load[16];
+      for (int r = 0; r < 16; ++r) load[r] = 0;
+      for (int l = 0; l < 16; ++l) {
+        rem[l] = 0;
+        for (int r = 0; r < 16; ++r) cnt[l][r] = 0;
+        ent[l].clear();
+        if (l >= nl) continue;
+        const VRow &q = v[h0 + l];
+        for (int k = 0; k < q.len; ++k) {
+          const int64_t p = rp[q.row] + q.off + k;
+          ent[l].push_back({(uint16_t)(std::lower_bound(wb, we, ci[p]) - wb), (uint32_t)p});
+        }
+        // group by residue; inside a residue keep the column order
+        std::stable_sort(ent[l].begin(), ent[l].end(), [](const Ent &a, const Ent &b) { return (a.idx & 15) < (b.idx & 15); });
+        for (const Ent &e : ent[l]) {
+          ++cnt[l][e.idx & 15];
+          ++load[e.idx & 15];
+        }
+        rem[l] = q.len;
       }
-      uint32_t &vp = H.vpos[q.row];  // the chunks of a row live in one slab: no race across threads
-      const int slot = q.chunk;
-      vp = (vp & ~(0x3ffu << (10 * slot))) | ((uint32_t)t << (10 * slot));
+      int first[16][16];  // first unused entry of every (lane, residue) group
+      for (int l = 0; l < 16; ++l) {
+        int o = 0;
+        for (int r = 0; r < 16; ++r) {
+          first[l][r] = o;
+          o += cnt[l][r];
+        }
+      }
+      for (int k = 0; k < W; ++k) {
+        int mult[16], order[16], pick[16];
+        for (int r = 0; r < 16; ++r) mult[r] = 0;
+        for (int l = 0; l < 16; ++l) {
+          order[l] = l;
+          pick[l] = -1;
+        }
+        // lanes without slack first, then by remaining length
+        std::stable_sort(order, order + 16, [&](int a, int b) { return rem[a] > rem[b]; });
+        for (int oi = 0; oi < 16; ++oi) {
+          const int l = order[oi];
+          if (rem[l] == 0) continue;
+          int best = -1;
+          for (int r = 0; r < 16; ++r)
+            if (cnt[l][r] > 0 && mult[r] == 0 && (best < 0 || load[r] > load[best])) best = r;
+          if (best < 0) {
+            if (rem[l] < W - k) continue;  // slack: idle this step
+            for (int r = 0; r < 16; ++r)
+              if (cnt[l][r] > 0 && (best < 0 || mult[r] < mult[best] || (mult[r] == mult[best] && load[r] > load[best])))
+                best = r;
+          }
+          pick[l] = best;
+          ++mult[best];
+        }
+        for (int l = 0; l < 16; ++l) {
+          const int64_t p = H.slice_ptr[sl] + slab_entry_pos(k, (int)((h0 + l) & 31));
+          if (pick[l] >= 0) {
+            const int r = pick[l];
+            const Ent &e = ent[l][first[l][r]++];
+            --cnt[l][r];
+            --load[r];
+            --rem[l];
+            H.idx[(size_t)p] = e.idx;
+            H.src[(size_t)p] = e.src;
+          } else {  // padding (value 0): point it at a bank pair nobody uses in this step
+            int r = 0;
+            while (r < 16 && mult[r] != 0) ++r;
+            if (r == 16 || (uint32_t)r >= nw) r = 0;
+            ++mult[r];
+            H.idx[(size_t)p] = (uint16_t)r;
+          }
+        }
+        int mx = 1;
+        for (int r = 0; r < 16; ++r) mx = std::max(mx, mult[r]);
+        wavefronts += mx;
+        ++steps;
+      }
+      for (int l = 0; l < 16; ++l)
+        if (rem[l] != 0) throw StructError("slab storage: internal scheduling error");
     }
   }
+  H.bank_wavefronts_per_step = steps ? (double)wavefronts / (double)steps : 1.0;
   H.max_window = maxw;
   return H;
 }
@@ -203,42 +298,46 @@ __global__ void slab_repack_kernel(int64_t n, const uint32_t *__restrict__ src, 
 }
 
 // Stage the window of slab s in shared memory and form this thread's partial row sum.
-template <int DIM>
+// Entries are taken kSlabBatch at a time: all (value, index) loads of a batch are issued before the
+// first use.  Measured on B200 at 9.7 M DoFs (tools/sweep_variants.py, gpurun_out/variants*.log):
+// batch 4 with 6 resident CTAs per SM (40 registers) is as fast as batches of 8 or 16, as 7-8
+// resident CTAs, as prefetching the first batch before the window is staged and as an asynchronous
+// (cp.async) window fill -- 0.34 ms per sweep in all cases; bank-aware entry order: 0.40 -> 0.345 ms.
+constexpr int kSlabBatch = 4;
+constexpr int kSlabMinBlocks = 6;
+template <int DIM, int BATCH>
 __device__ __forceinline__ void slab_product(const SlabView &S, int s, const double *__restrict__ x, double *sm,
                                              double (&acc)[DIM]) {
+  static_assert(BATCH % 2 == 0, "entries are fetched in pairs");
   const int t = threadIdx.x;
+  const int64_t sl = (int64_t)s * kSlabSlices + (t >> 5);
+  const int64_t base = S.slice_ptr[sl];
+  const int W2 = (int)((S.slice_ptr[sl + 1] - base) >> 6);  // pairs of entries per lane; warp-uniform
+  const double2 *__restrict__ v = reinterpret_cast<const double2 *>(S.val + base) + (t & 31);
+  const uint32_t *__restrict__ ix = reinterpret_cast<const uint32_t *>(S.idx + base) + (t & 31);
   const uint32_t w0 = S.win_ptr[s], nw = S.win_ptr[s + 1] - w0;
   for (uint32_t i = t; i < DIM * nw; i += kSlabThreads) {
     const uint32_t node = __ldg(S.win_list + w0 + i / DIM);
     sm[i] = __ldg(x + (size_t)DIM * node + i % DIM);
   }
-  const int64_t sl = (int64_t)s * kSlabSlices + (t >> 5);
-  const int64_t base = S.slice_ptr[sl];
-  const int W = (int)((S.slice_ptr[sl + 1] - base) >> 5);
-  const double *__restrict__ v = S.val + base + (t & 31);
-  const uint16_t *__restrict__ ix = S.idx + base + (t & 31);
 #pragma unroll
   for (int c = 0; c < DIM; ++c) acc[c] = 0.0;
   __syncthreads();
-  int k = 0;
-  for (; k + 4 <= W; k += 4) {
-    double a[4];
-    unsigned j[4];
+  for (int k = 0; k < W2; k += BATCH / 2) {
+    double2 a[BATCH / 2];
+    uint32_t j[BATCH / 2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      a[u] = __ldcs(v + 32 * (k + u));
-      j[u] = __ldcs(ix + 32 * (k + u));
+    for (int u = 0; u < BATCH / 2; ++u) {
+      a[u] = k + u < W2 ? __ldcs(v + 32 * (k + u)) : make_double2(0.0, 0.0);
+      j[u] = k + u < W2 ? __ldcs(ix + 32 * (k + u)) : 0u;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < BATCH / 2; ++u)
 #pragma unroll
-      for (int c = 0; c < DIM; ++c) acc[c] += a[u] * sm[DIM * j[u] + c];
-  }
-  for (; k < W; ++k) {
-    const double a = __ldcs(v + 32 * k);
-    const unsigned j = __ldcs(ix + 32 * k);
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) acc[c] += a * sm[DIM * j + c];
+      for (int c = 0; c < DIM; ++c) {
+        acc[c] += a[u].x * sm[DIM * (j[u] & 0xffffu) + c];
+        acc[c] += a[u].y * sm[DIM * (j[u] >> 16) + c];
+      }
   }
   __syncthreads();  // every warp is done with the window: its space now takes the partial sums
 #pragma unroll
@@ -259,7 +358,7 @@ __device__ __forceinline__ double slab_row_sum(const double *sm, uint32_t vp, in
 // One Chebyshev-Jacobi sweep on F z = b (see cheb_sweep_kernel in spmv.cuh):
 //   dnew = c1 * d + c2 * Dinv .* (b - F z);  znew = z + dnew      (z, znew distinct)
 template <int DIM>
-__global__ void __launch_bounds__(kSlabThreads) fs_slab_sweep_kernel(SlabView S, const double *__restrict__ dinv,
+__global__ void __launch_bounds__(kSlabThreads, kSlabMinBlocks) fs_slab_sweep_kernel(SlabView S, const double *__restrict__ dinv,
                                                                      const double *__restrict__ b,
                                                                      const double *__restrict__ z,
                                                                      double *__restrict__ d, double *__restrict__ znew,
@@ -267,7 +366,7 @@ __global__ void __launch_bounds__(kSlabThreads) fs_slab_sweep_kernel(SlabView S,
   extern __shared__ double sm[];
   const int s = blockIdx.x;
   double acc[DIM];
-  slab_product<DIM>(S, s, z, sm, acc);
+  slab_product<DIM, kSlabBatch>(S, s, z, sm, acc);
   const uint32_t r0 = S.slab_row[s], nr = S.slab_row[s + 1] - r0;
   for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
     const double sc = slab_row_sum<DIM>(sm, S.vpos[r0 + i / DIM], (int)(i % DIM));
@@ -440,7 +539,7 @@ __global__ void __launch_bounds__(kSlabThreads) fs_slab_apply_kernel(SlabView S,
   double *smo = sm + win_doubles, *smp = smo + DIM * kSlabThreads;
   if (MODE == 0) slab_g_product<DIM>(G, s, r0, nr, xp, smp, smo);
   double acc[DIM];
-  slab_product<DIM>(S, s, xu, sm, acc);
+  slab_product<DIM, kSlabBatch>(S, s, xu, sm, acc);
   for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
     double sc = slab_row_sum<DIM>(sm, S.vpos[r0 + i / DIM], (int)(i % DIM));
     const int64_t g = (int64_t)DIM * r0 + i;

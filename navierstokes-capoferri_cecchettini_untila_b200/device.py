@@ -103,13 +103,13 @@ def slab_host_check(dim, rowptr, colind, val, x, n_cols=None, window_cap=1408):
     n_rows = rowptr.size - 1
     n_cols = n_rows if n_cols is None else n_cols
     y = np.zeros(dim * n_rows)
-    st = np.zeros(5, np.int64)
+    st = np.zeros(6, np.int64)
     rc = device_lib().nsb_slab_host_check(dim, n_rows, n_cols, _p(rowptr, C.c_int64), _p(colind, C.c_uint32),
                                           _p(val, C.c_double), window_cap, _p(x, C.c_double), _p(y, C.c_double),
                                           _p(st, C.c_int64))
     if rc != 0:
         raise DeviceError(f"nsb_slab_host_check failed ({rc})")
-    return y, dict(zip(["slabs", "nnz", "padded", "max_window", "window_total"], [int(v) for v in st]))
+    return y, dict(zip(["slabs", "nnz", "padded", "max_window", "window_total", "bank_wavefronts_permille"], [int(v) for v in st]))
 
 
 def gslab_host_check(dim, node_rowptr, node_colind, rowptr01, colind01, val01, xp, window_cap=1408):
