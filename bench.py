@@ -135,9 +135,10 @@ def spmv_bytes(info, dim=3):
 
 
 def sweep_bytes(info, dim=3):
-    """One Chebyshev-Jacobi sweep on F: F_s stream + z read once (window staging; re-reads hit L2)
-    + b, dinv, d read and d, znew written."""
-    return fs_slab_bytes(info, dim) + 8 * info["n_u"] * 6
+    """One Chebyshev-Jacobi sweep on F (three-term form): F_s stream + z read once (window staging;
+    re-reads hit L2) + zold, Dinv.*b read, znew written, Dinv read per node."""
+    n_u = info["n_u"]
+    return fs_slab_bytes(info, dim) + 8 * n_u * 4 + 8 * (n_u // dim)
 
 
 def sweep_s_bytes(info):

@@ -71,7 +71,8 @@ struct nsb_ctx {
   GSlabDev gslab;                // A01 in the same slabs
   size_t fslab_smem = 0, fapply_smem = 0, gapply_smem = 0;  // dynamic shared memory of the slab kernels
   uint32_t fslab_win_doubles = 0;
-  DevBuf<double> chzA, chzB;     // Chebyshev iterates on F (ping-pong)
+  DevBuf<double> chzA, chzB;     // Chebyshev iterates on F (rotating with chz_u; chd_u holds Dinv .* b)
+  DevBuf<double> din;            // 1 / diag(F_s) per owned node
   // The preconditioner application is a fixed sequence of ~100 short launches per outer iteration: it is
   // captured into a CUDA graph once per time step (tmpN -> pz) and replayed (NSB_GRAPH=0 disables).
   DevBuf<double> pz;
@@ -314,34 +315,41 @@ void g_apply(nsb_ctx *c, const double *xp, const double *w, const double *d, dou
                     w, d, y);
 }
 
-void fs_cheb_sweep(nsb_ctx *c, const double *dinv, const double *b, const double *z, double *d, double *znew, double c1,
-                   double c2) {
+void fs_cheb_sweep(nsb_ctx *c, const double *bd, const double *z, const double *zold, double *znew, double c1, double c2) {
   const unsigned grid = (unsigned)c->fslab.n_slabs;
   const SlabView S = c->fslab.view();
   if (c->dim == 2)
-    NSB_LAUNCH_SMEM(c, fs_slab_sweep_kernel<2>, grid, kSlabThreads, c->fslab_smem, S, dinv, b, z, d, znew, c1, c2);
+    NSB_LAUNCH_SMEM(c, fs_slab_sweep_kernel<2>, grid, kSlabThreads, c->fslab_smem, S, c->din.p, bd, z, zold, znew, c1, c2);
   else
-    NSB_LAUNCH_SMEM(c, fs_slab_sweep_kernel<3>, grid, kSlabThreads, c->fslab_smem, S, dinv, b, z, d, znew, c1, c2);
+    NSB_LAUNCH_SMEM(c, fs_slab_sweep_kernel<3>, grid, kSlabThreads, c->fslab_smem, S, c->din.p, bd, z, zold, znew, c1, c2);
 }
 
-// vec ~= F^{-1} b: degree-k Chebyshev-Jacobi polynomial on F, zero initial guess; the last sweep writes `out`.
-void cheb_solve_F(nsb_ctx *c, const double *b, double *out, double *d, int k, double lmax, double ratio) {
+// out ~= F^{-1} b: degree-k Chebyshev-Jacobi polynomial on F, zero initial guess, three-term recurrence
+//   z_1 = Dinv b / theta,  z_{i+1} = z_i + rho_{i+1} rho_i (z_i - z_{i-1}) + (2 rho_{i+1} / delta) Dinv (b - F z_i)
+// The iterates rotate through three buffers; the last sweep writes `out`.
+void cheb_solve_F(nsb_ctx *c, const double *b, double *out, int k, double lmax, double ratio) {
   const int64_t n = c->n_u;
-  const double *dinv = c->di.p;
   const double lmin = lmax / ratio, theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
-  if (k <= 1) {
-    NSB_LAUNCH(c, cheb_first_kernel, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, out);
-    return;
-  }
-  double *z = c->chzA.p, *zn = c->chzB.p;
-  NSB_LAUNCH(c, cheb_first_kernel, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, z);
+  double *bd = c->chd_u.p;
+  double *z = k <= 1 ? out : c->chzA.p, *zold = c->chzB.p, *znew = c->chz_u.p;
+  if (c->dim == 2)
+    NSB_LAUNCH(c, fs_cheb_first_kernel<2>, blocks_for(n), 256, n, c->din.p, b, 1.0 / theta, bd, z);
+  else
+    NSB_LAUNCH(c, fs_cheb_first_kernel<3>, blocks_for(n), 256, n, c->din.p, b, 1.0 / theta, bd, z);
+  if (k <= 1) return;
+  NSB_CUDA(cudaMemsetAsync(zold, 0, (size_t)n * sizeof(double), c->stream));  // z_0 = 0
   double rho = 1.0 / sigma;
   for (int i = 1; i < k; ++i) {
     const double rho_new = 1.0 / (2.0 * sigma - rho);
     const bool last = i == k - 1;
     halo_exchange(c, z);
-    fs_cheb_sweep(c, dinv, b, z, d, last ? out : zn, rho_new * rho, 2.0 * rho_new / delta);
-    std::swap(z, zn);
+    double *target = last ? out : znew;
+    fs_cheb_sweep(c, bd, z, zold, target, rho_new * rho, 2.0 * rho_new / delta);
+    // rotate: zold <- z, z <- target, the old zold becomes the next target
+    double *freed = zold;
+    zold = z;
+    z = target;
+    znew = freed;
     rho = rho_new;
   }
 }
@@ -646,6 +654,7 @@ void finalize_setup(nsb_ctx *c) {
   dz(c->force_out, 2);
   dz(c->mdiag, (size_t)c->n_own_nodes);
   dz(c->chzA, c->n_uloc);
+  dz(c->din, c->n_own_nodes);
   dz(c->chzB, c->n_uloc);
   if (c->send_ptr.size() > 1 && c->send_ptr.back() > 0)
     c->send_buf.alloc((size_t)c->send_ptr.back() * c->dim, &c->dev_bytes);
@@ -883,6 +892,8 @@ void prec_init(nsb_ctx *c) {
   auto_inner(c);
   NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_u), 256, (int64_t)c->n_u, c->dim, c->fs.val.p, c->diagF.p,
              c->di.p);
+  NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_own_nodes), 256, (int64_t)c->n_own_nodes, 1, c->fs.val.p, c->diagF.p,
+             c->din.p);
   if (c->prec != NSB_PREC_ASIMPLE) return;
   c->s.val.zero(c->stream);
   NSB_LAUNCH(c, schur_outer_kernel, blocks_for((int64_t)c->n_u * 32), 256, c->a01.view(), c->a10t.p, c->di.p,
@@ -909,7 +920,7 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
     return;
   }
   // vec0 ~= F^-1 src0                                   (:978-981)
-  cheb_solve_F(c, src, c->vec0.p, c->chd_u.p, c->kF, c->lamF, c->rF);
+  cheb_solve_F(c, src, c->vec0.p, c->kF, c->lamF, c->rF);
   // vec1 = src1 - B vec0                                 (:982-983)
   halo_exchange(c, c->vec0.p);
   spmv(c, c->a10, 1, c->vec0.p, src + c->n_uloc + c->p_begin, nullptr, c->vec1.p + c->p_begin);
@@ -1554,7 +1565,7 @@ int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
           NSB_LAUNCH(c, schur_outer_kernel, blocks_for((int64_t)c->n_u * 32), 256, c->a01.view(), c->a10t.p, c->di.p,
                      c->s.view());
           break;
-        case 4: fs_cheb_sweep(c, c->di.p, c->rhs.p, c->chzA.p, c->chd_u.p, c->chzB.p, 0.5, 0.5); break;
+        case 4: fs_cheb_sweep(c, c->chd_u.p, c->chzA.p, c->chzB.p, c->chz_u.p, 0.5, 0.5); break;
         case 6: cheb_sweep(c, c->s, c->dis.p, c->vec1.p, c->chz_p.p, c->chd_p.p, c->chz_p2.p, 0.5, 0.5); break;
         default: throw ArgError("nsb_bench_kernel: unknown kernel id");
       }
@@ -1636,6 +1647,7 @@ int nsb_slab_host_check(int dim, int64_t n_rows, int64_t n_cols, const int64_t *
     stats[3] = H.max_window;
     stats[4] = (int64_t)H.win_list.size();
     stats[5] = (int64_t)std::llround(1000.0 * H.bank_wavefronts_per_step);
+    if (std::getenv("NSB_SLAB_DEBUG")) std::fprintf(stderr, "slab: wavefronts/step %.3f bound %.3f\n", H.bank_wavefronts_per_step, H.bank_wavefronts_bound);
     return NSB_OK;
   } catch (const StructError &) {
     return NSB_ESTRUCT;

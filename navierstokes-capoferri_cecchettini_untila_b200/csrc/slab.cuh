@@ -65,6 +65,7 @@ struct SlabHost {
   uint32_t max_window = 0;
   int64_t nnz = 0;
   double bank_wavefronts_per_step = 1.0;  // shared-memory wavefronts per half-warp load (1 = conflict-free)
+  double bank_wavefronts_bound = 1.0;     // lower bound for this window order (most loaded residue per half-warp)
 };
 
 struct SlabDev {
@@ -164,8 +165,8 @@ inline SlabHost build_slabs(int64_t n_rows, int64_t n_cols, const int64_t *rp, c
   // slack in its slice, and only otherwise accepts a bank conflict.  ncu before this ordering: 2.2
   // conflict wavefronts per shared load, L1/shared pipe the busiest unit of the sweep kernel at 73 %.
   uint32_t maxw = 0;
-  int64_t wavefronts = 0, steps = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(max : maxw) reduction(+ : wavefronts, steps)
+  int64_t wavefronts = 0, steps = 0, bound = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : maxw) reduction(+ : wavefronts, steps, bound)
   for (int64_t s = 0; s < ns; ++s) {
     const uint32_t *wb = H.win_list.data() + H.win_ptr[s], *we = H.win_list.data() + H.win_ptr[s + 1];
     const uint32_t nw = (uint32_t)(we - wb);
@@ -203,6 +204,11 @@ inline SlabHost build_slabs(int64_t n_rows, int64_t n_cols, const int64_t *rp, c
           ++load[e.idx & 15];
         }
         rem[l] = q.len;
+      }
+      {
+        int mxl = W;
+        for (int r = 0; r < 16; ++r) mxl = std::max(mxl, load[r]);
+        bound += mxl;
       }
       int first[16][16];  // first unused entry of every (lane, residue) group
       for (int l = 0; l < 16; ++l) {
@@ -264,6 +270,7 @@ inline SlabHost build_slabs(int64_t n_rows, int64_t n_cols, const int64_t *rp, c
     }
   }
   H.bank_wavefronts_per_step = steps ? (double)wavefronts / (double)steps : 1.0;
+  H.bank_wavefronts_bound = steps ? (double)bound / (double)steps : 1.0;
   H.max_window = maxw;
   return H;
 }
@@ -355,28 +362,41 @@ __device__ __forceinline__ double slab_row_sum(const double *sm, uint32_t vp, in
   return s;
 }
 
-// One Chebyshev-Jacobi sweep on F z = b (see cheb_sweep_kernel in spmv.cuh):
-//   dnew = c1 * d + c2 * Dinv .* (b - F z);  znew = z + dnew      (z, znew distinct)
+// One Chebyshev-Jacobi sweep on F z = b in three-term form (d_k = z_k - z_{k-1} is not stored):
+//   znew = z + c1 * (z - zold) + c2 * (bd - Dinv .* (F z)),   bd = Dinv .* b (formed once per solve)
+// Dinv is kept per NODE (the diagonal of A00 = F_s (x) I_dim is the same for the dim components), so
+// the vector traffic of a sweep is z, zold, bd read and znew written: 4 1/3 streams instead of the 6
+// (b, Dinv, d read; d, znew written; z) of the two-term form.  z, zold, znew are distinct buffers.
 template <int DIM>
-__global__ void __launch_bounds__(kSlabThreads, kSlabMinBlocks) fs_slab_sweep_kernel(SlabView S, const double *__restrict__ dinv,
-                                                                     const double *__restrict__ b,
-                                                                     const double *__restrict__ z,
-                                                                     double *__restrict__ d, double *__restrict__ znew,
-                                                                     double c1, double c2) {
+__global__ void __launch_bounds__(kSlabThreads, kSlabMinBlocks)
+    fs_slab_sweep_kernel(SlabView S, const double *__restrict__ dinv_node, const double *__restrict__ bd,
+                         const double *__restrict__ z, const double *__restrict__ zold, double *__restrict__ znew,
+                         double c1, double c2) {
   extern __shared__ double sm[];
   const int s = blockIdx.x;
   double acc[DIM];
   slab_product<DIM, kSlabBatch>(S, s, z, sm, acc);
   const uint32_t r0 = S.slab_row[s], nr = S.slab_row[s + 1] - r0;
   for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
-    const double sc = slab_row_sum<DIM>(sm, S.vpos[r0 + i / DIM], (int)(i % DIM));
+    const uint32_t r = r0 + i / DIM;
+    const double sc = slab_row_sum<DIM>(sm, S.vpos[r], (int)(i % DIM));
     const int64_t g = (int64_t)DIM * r0 + i;
-    const double dn = c1 * d[g] + c2 * dinv[g] * (b[g] - sc);
-    d[g] = dn;
-    znew[g] = __ldg(z + g) + dn;
+    const double zg = __ldg(z + g);
+    znew[g] = zg + c1 * (zg - zold[g]) + c2 * (bd[g] - dinv_node[r] * sc);
   }
 }
 
+// first sweep on F with zero initial guess: bd = Dinv .* b, z1 = bd / theta
+template <int DIM>
+__global__ void fs_cheb_first_kernel(int64_t n_u, const double *__restrict__ dinv_node, const double *__restrict__ b,
+                                     double inv_theta, double *__restrict__ bd, double *__restrict__ z1) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_u) {
+    const double v = dinv_node[i / DIM] * b[i];
+    bd[i] = v;
+    z1[i] = v * inv_theta;
+  }
+}
 
 // ---------------------------------------------------------------------------
 // A01 (velocity rows x pressure columns, reference system_matrix.block(0,1)) in
