@@ -127,10 +127,12 @@ def fs_slab_bytes(info, dim=3):
 
 
 def spmv_bytes(info, dim=3):
-    """y = A x on the storage the solver uses: F_s and A01 in slab form (10 B per stored
-    non-zero + windows + 2 B row permutation per A01 row), A10 as CSR; x read once, y written once."""
+    """y = A x on the storage the solver uses: F_s in slab form, A01 in node-block slab form (8 B per
+    value + 2 B index per node-level entry + pressure windows + 2 B permutation per node), A10 as
+    CSR; x read once, y written once.  ELL padding is not counted."""
     n_u, n_p = info["n_u"], info["n_p"]
-    g = 10 * info["nnz_a01"] + 4 * info["gslab_window_total"] + 2 * n_u + 8 * 24 * info["slab_count"]
+    g = 8 * info["nnz_a01"] + 2 * (info["nnz_a01"] // dim) + 4 * info["gslab_window_total"] + 2 * (n_u // dim) \
+        + 8 * 8 * info["slab_count"]
     return fs_slab_bytes(info, dim) + g + 12 * info["nnz_a10"] + 8 * (n_p + 1) + 16 * (n_u + n_p)
 
 

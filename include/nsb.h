@@ -125,8 +125,8 @@ int nsb_vmult(nsb_ctx *ctx, const double *x_host, double *y_host);
  * which: 0 block SpMV y=Ax on the canonical (reference) CSR, 1 assembly
  * (zero + cell loop + Dirichlet rows), 2 preconditioner apply, 3 S = B Di Bt,
  * 4 Chebyshev sweep on F (node-block storage), 5 block SpMV on the compressed
- * storage the solver uses, 6 Chebyshev sweep on S.  Add 0x100 to flush L2
- * between repetitions. */
+ * storage the solver uses, 6 Chebyshev sweep on S, 7 dst0 = vec0 - Di .* (A01 p), 8 vec1 = src1 - A10 u.
+ * Add 0x100 to flush L2 between repetitions. */
 int nsb_bench_kernel(nsb_ctx *ctx, int which, int reps, double *ms_mean);
 /* Launch counter of this context's own kernels (for bench.py gpu_launches). */
 int64_t nsb_launch_count(const nsb_ctx *ctx);

@@ -1567,6 +1567,8 @@ int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
           break;
         case 4: fs_cheb_sweep(c, c->chd_u.p, c->chzA.p, c->chzB.p, c->chz_u.p, 0.5, 0.5); break;
         case 6: cheb_sweep(c, c->s, c->dis.p, c->vec1.p, c->chz_p.p, c->chd_p.p, c->chz_p2.p, 0.5, 0.5); break;
+        case 7: g_apply(c, c->sol.p + c->n_uloc, c->vec0.p, c->di.p, c->tmpN.p); break;
+        case 8: spmv(c, c->a10, 1, c->vec0.p, c->rhs.p + c->n_uloc + c->p_begin, nullptr, c->vec1.p + c->p_begin); break;
         default: throw ArgError("nsb_bench_kernel: unknown kernel id");
       }
       NSB_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -1667,21 +1669,23 @@ int nsb_gslab_host_check(int dim, int64_t n_nodes, int64_t n_node_cols, const in
     const int64_t ns = (int64_t)H.slab_row.size() - 1;
     for (int64_t s = 0; s < ns; ++s) {  // what slab_g_product does
       const uint32_t w0 = G.pwin_ptr[s];
-      const int64_t d0 = (int64_t)dim * H.slab_row[s], nd = (int64_t)dim * (H.slab_row[s + 1] - H.slab_row[s]);
-      for (int64_t i = 0; i < nd; ++i) {
-        const int64_t sl = s * kGSlices + i / 32, base = G.slice_ptr[sl] + i % 32;
-        const int W = (int)((G.slice_ptr[sl + 1] - G.slice_ptr[sl]) >> 5);
-        double a0 = 0.0;
-        for (int k = 0; k < W; ++k) {
-          const int64_t p = base + 32 * (int64_t)k;
-          const double v = G.src[p] != kSlabPad ? val01[G.src[p]] : 0.0;
-          a0 += v * xp[G.pwin_list[w0 + G.idx[p]]];
+      const int64_t a0 = H.slab_row[s], na = (int64_t)H.slab_row[s + 1] - a0;
+      for (int64_t i = 0; i < na; ++i) {
+        const int64_t sl = s * kSlabSlices + i / 32, base = G.slice_ptr[sl];
+        const int W = (int)((G.slice_ptr[sl + 1] - base) >> 5), lane = (int)(i % 32);
+        for (int c = 0; c < dim; ++c) {
+          double acc = 0.0;
+          for (int k = 0; k < W; ++k) {
+            const uint32_t sp = G.src[(size_t)gslab_val_pos(dim, base, k, c, lane)];
+            const double v = sp != kSlabPad ? val01[sp] : 0.0;
+            acc += v * xp[G.pwin_list[w0 + G.idx[(size_t)(base + 32 * k + lane)]]];
+          }
+          y[dim * (a0 + G.perm[(size_t)(a0 + i)]) + c] = acc;
         }
-        y[d0 + G.perm[(size_t)(d0 + i)]] = a0;
       }
     }
     stats[0] = G.nnz;
-    stats[1] = G.slice_ptr.back();
+    stats[1] = (int64_t)G.src.size();
     stats[2] = G.max_window;
     return NSB_OK;
   } catch (const StructError &) {

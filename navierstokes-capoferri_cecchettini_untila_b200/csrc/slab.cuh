@@ -400,22 +400,29 @@ __global__ void fs_cheb_first_kernel(int64_t n_u, const double *__restrict__ din
 
 // ---------------------------------------------------------------------------
 // A01 (velocity rows x pressure columns, reference system_matrix.block(0,1)) in
-// the same slabs.  The dof rows [dim*r0, dim*r1) of a slab are sorted by length
-// (a vertex node couples to ~15 pressure vertices, an edge node to ~7) and
-// stored as ELL slices of 32 rows with a 16-bit index into the slab's PRESSURE
-// window, which is staged in shared memory like the velocity window.  `perm`
-// maps the sorted position back to the natural dof of the slab so that results
-// are handed over through shared memory and written coalesced.
+// the same slabs, in NODE-BLOCK form: the dim rows of a velocity node have the
+// same pattern, so an entry is (pressure column, dim values) -- 8*dim + 2 B
+// instead of dim * 12 B in CSR.  The nodes of a slab are sorted by the length
+// of their rows (a vertex node couples to ~15 pressure vertices, an edge node
+// to ~7) and stored as ELL slices of 32 nodes: thread t of the CTA owns the
+// t-th node in that order and streams, per entry, dim coalesced value loads and
+// a 16-bit index into the slab's PRESSURE window, which is staged in shared
+// memory like the velocity window.  `perm` maps the sorted position back to the
+// natural node of the slab so that results are handed over through shared
+// memory and written coalesced.
 // ---------------------------------------------------------------------------
-constexpr int kGSlices = 3 * kSlabThreads / 32;  // dof rows of one slab / 32, at most (dim <= 3)
+#ifndef NSB_G_BATCH
+#define NSB_G_BATCH 2
+#endif
+constexpr int kGSlabBatch = NSB_G_BATCH;
 
 struct GSlabView {
   const uint32_t *pwin_ptr;   // n_slabs+1
   const uint32_t *pwin_list;  // pressure columns, ascending inside a slab
-  const int64_t *slice_ptr;   // n_slabs*kGSlices+1
-  const double *val;
+  const int64_t *slice_ptr;   // n_slabs*kSlabSlices+1, in entries (multiples of 32); values at dim * offset
+  const double *val;          // per slice and entry step k: dim x 32 values, component-major
   const uint16_t *idx;
-  const uint16_t *perm;       // per dof row (slab-major, sorted position) -> natural local dof of the slab
+  const uint16_t *perm;       // per node (slab-major, sorted position) -> natural local node of the slab
 };
 
 struct GSlabHost {
@@ -427,7 +434,7 @@ struct GSlabHost {
 };
 
 struct GSlabDev {
-  int64_t nnz = 0, padded = 0;
+  int64_t nnz = 0, padded = 0;  // scalar values stored / incl. padding
   uint32_t max_window = 0;
   DevBuf<uint32_t> pwin_ptr, pwin_list, src;
   DevBuf<int64_t> slice_ptr;
@@ -437,57 +444,67 @@ struct GSlabDev {
   GSlabView view() const { return {pwin_ptr.p, pwin_list.p, slice_ptr.p, val.p, idx.p, perm.p}; }
 };
 
+// position of value (step k, component c, lane) of a slice that starts at entry offset `base`
+__host__ __device__ inline int64_t gslab_val_pos(int dim, int64_t base, int k, int c, int lane) {
+  return (int64_t)dim * base + ((int64_t)k * dim + c) * 32 + lane;
+}
+
 // rp/ci: CSR pattern of A01 (one row per velocity dof, dim rows per node, in node order)
 inline GSlabHost build_gslabs(int dim, const std::vector<uint32_t> &slab_row, const int64_t *rp, const uint32_t *ci) {
   GSlabHost H;
   const int64_t ns = (int64_t)slab_row.size() - 1;
-  const int64_t n_rows = (int64_t)dim * slab_row.back();
-  H.nnz = rp[n_rows];
+  const int64_t n_nodes = slab_row.back();
+  H.nnz = rp[(int64_t)dim * n_nodes];
   if (H.nnz >= (int64_t)kSlabPad) throw ArgError("slab storage: more than 2^32-2 stored entries per rank");
+  for (int64_t a = 0; a < n_nodes; ++a)
+    for (int c = 1; c < dim; ++c)
+      if (rp[dim * a + c + 1] - rp[dim * a + c] != rp[dim * a + 1] - rp[dim * a])
+        throw StructError("A01: the rows of a velocity node do not have the same pattern");
   std::vector<std::vector<uint32_t>> wins((size_t)ns);
-  std::vector<int64_t> slice_len((size_t)ns * kGSlices, 0);
-  H.perm.assign((size_t)n_rows, 0);
+  std::vector<int64_t> slice_len((size_t)ns * kSlabSlices, 0);
+  H.perm.assign((size_t)n_nodes, 0);
   uint32_t maxw = 0;
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : maxw)
   for (int64_t s = 0; s < ns; ++s) {
-    const int64_t d0 = (int64_t)dim * slab_row[s], nd = (int64_t)dim * (slab_row[s + 1] - slab_row[s]);
+    const int64_t a0 = slab_row[s], na = (int64_t)slab_row[s + 1] - a0;
+    if (na > kSlabThreads) throw StructError("slab storage: more nodes than threads in a slab");
     std::vector<uint32_t> &w = wins[s];
-    w.assign(ci + rp[d0], ci + rp[d0 + nd]);
+    for (int64_t a = a0; a < a0 + na; ++a) w.insert(w.end(), ci + rp[dim * a], ci + rp[dim * a + 1]);
     std::sort(w.begin(), w.end());
     w.erase(std::unique(w.begin(), w.end()), w.end());
     if (w.size() > 65535) throw StructError("slab storage: pressure window exceeds 16-bit indices");
     maxw = std::max(maxw, (uint32_t)w.size());
-    std::vector<uint16_t> order((size_t)nd);
-    for (int64_t i = 0; i < nd; ++i) order[i] = (uint16_t)i;
-    std::stable_sort(order.begin(), order.end(), [&](uint16_t a, uint16_t b) {
-      return rp[d0 + a + 1] - rp[d0 + a] > rp[d0 + b + 1] - rp[d0 + b];
-    });
-    for (int64_t i = 0; i < nd; ++i) H.perm[(size_t)(d0 + i)] = order[i];
-    for (int64_t wv = 0; wv * 32 < nd; ++wv) {
-      const int64_t r = d0 + order[wv * 32];
-      slice_len[s * kGSlices + wv] = 32 * (rp[r + 1] - rp[r]);
-    }
+    std::vector<uint16_t> order((size_t)na);
+    for (int64_t i = 0; i < na; ++i) order[i] = (uint16_t)i;
+    auto len = [&](int64_t a) { return rp[dim * a + 1] - rp[dim * a]; };
+    std::stable_sort(order.begin(), order.end(), [&](uint16_t x, uint16_t y) { return len(a0 + x) > len(a0 + y); });
+    for (int64_t i = 0; i < na; ++i) H.perm[(size_t)(a0 + i)] = order[i];
+    for (int64_t wv = 0; wv * 32 < na; ++wv) slice_len[s * kSlabSlices + wv] = 32 * len(a0 + order[wv * 32]);
   }
   H.max_window = maxw;
   H.pwin_ptr.assign((size_t)ns + 1, 0);
   for (int64_t s = 0; s < ns; ++s) H.pwin_ptr[s + 1] = H.pwin_ptr[s] + (uint32_t)wins[s].size();
   H.pwin_list.resize(H.pwin_ptr.back());
-  H.slice_ptr.assign((size_t)ns * kGSlices + 1, 0);
+  H.slice_ptr.assign((size_t)ns * kSlabSlices + 1, 0);
   for (size_t i = 0; i < slice_len.size(); ++i) H.slice_ptr[i + 1] = H.slice_ptr[i] + slice_len[i];
   H.idx.assign((size_t)H.slice_ptr.back(), 0);
-  H.src.assign((size_t)H.slice_ptr.back(), kSlabPad);
+  H.src.assign((size_t)H.slice_ptr.back() * dim, kSlabPad);
 #pragma omp parallel for schedule(dynamic, 64)
   for (int64_t s = 0; s < ns; ++s) {
     const std::vector<uint32_t> &w = wins[s];
     std::copy(w.begin(), w.end(), H.pwin_list.begin() + H.pwin_ptr[s]);
-    const int64_t d0 = (int64_t)dim * slab_row[s], nd = (int64_t)dim * (slab_row[s + 1] - slab_row[s]);
-    for (int64_t i = 0; i < nd; ++i) {
-      const int64_t r = d0 + H.perm[(size_t)(d0 + i)];
-      const int64_t base = H.slice_ptr[s * kGSlices + i / 32] + i % 32;
-      for (int64_t k = rp[r]; k < rp[r + 1]; ++k) {
-        const int64_t p = base + 32 * (k - rp[r]);
-        H.idx[(size_t)p] = (uint16_t)(std::lower_bound(w.begin(), w.end(), ci[k]) - w.begin());
-        H.src[(size_t)p] = (uint32_t)k;
+    const int64_t a0 = slab_row[s], na = (int64_t)slab_row[s + 1] - a0;
+    for (int64_t i = 0; i < na; ++i) {
+      const int64_t a = a0 + H.perm[(size_t)(a0 + i)];
+      const int64_t base = H.slice_ptr[s * kSlabSlices + i / 32];
+      const int lane = (int)(i % 32);
+      const int64_t r0 = rp[dim * a], n = rp[dim * a + 1] - r0;
+      for (int64_t k = 0; k < n; ++k) {
+        H.idx[(size_t)(base + 32 * k + lane)] = (uint16_t)(std::lower_bound(w.begin(), w.end(), ci[r0 + k]) - w.begin());
+        for (int c = 0; c < dim; ++c) {
+          if (ci[rp[dim * a + c] + k] != ci[r0 + k]) throw StructError("A01: the rows of a velocity node do not have the same pattern");
+          H.src[(size_t)gslab_val_pos(dim, base, (int)k, c, lane)] = (uint32_t)(rp[dim * a + c] + k);
+        }
       }
     }
   }
@@ -496,7 +513,7 @@ inline GSlabHost build_gslabs(int dim, const std::vector<uint32_t> &slab_row, co
 
 inline void upload_gslabs(const GSlabHost &H, GSlabDev &D, cudaStream_t s, int64_t *bytes) {
   D.nnz = H.nnz;
-  D.padded = H.slice_ptr.back();
+  D.padded = (int64_t)H.src.size();
   D.max_window = H.max_window;
   D.pwin_ptr.upload(H.pwin_ptr.data(), H.pwin_ptr.size(), s, bytes);
   D.pwin_list.upload(H.pwin_list.data(), H.pwin_list.size(), s, bytes);
@@ -510,36 +527,44 @@ inline void upload_gslabs(const GSlabHost &H, GSlabDev &D, cudaStream_t s, int64
   D.have = true;
 }
 
-// smo[natural local dof] = (A01 xp)[dof] for the dof rows of slab s.  smp: pressure window, smo: dim*nr doubles.
-// Ends with a __syncthreads().
+// smo[dim * natural local node + c] = (A01 xp)[dof] for the rows of slab s.  smp: pressure window,
+// smo: dim*nr doubles.  Ends with a __syncthreads().
 template <int DIM>
 __device__ __forceinline__ void slab_g_product(const GSlabView &G, int s, uint32_t r0, uint32_t nr,
                                                const double *__restrict__ xp, double *smp, double *smo) {
   const int t = threadIdx.x;
   const uint32_t w0 = G.pwin_ptr[s], nw = G.pwin_ptr[s + 1] - w0;
   for (uint32_t i = t; i < nw; i += kSlabThreads) smp[i] = __ldg(xp + __ldg(G.pwin_list + w0 + i));
+  const int64_t sl = (int64_t)s * kSlabSlices + (t >> 5);
+  const int64_t base = G.slice_ptr[sl];
+  const int W = (int)((G.slice_ptr[sl + 1] - base) >> 5);  // warp-uniform; 0 for warps beyond the last node
+  const double *__restrict__ v = G.val + (int64_t)DIM * base + (t & 31);
+  const uint16_t *__restrict__ ix = G.idx + base + (t & 31);
+  double acc[DIM];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) acc[c] = 0.0;
   __syncthreads();
-  const uint32_t nd = DIM * nr;
-  for (uint32_t i = t; i < nd; i += kSlabThreads) {  // i >> 5 is warp-uniform
-    const int64_t sl = (int64_t)s * kGSlices + (i >> 5);
-    const int64_t base = G.slice_ptr[sl];
-    const int W = (int)((G.slice_ptr[sl + 1] - base) >> 5);
-    const double *__restrict__ v = G.val + base + (t & 31);
-    const uint16_t *__restrict__ ix = G.idx + base + (t & 31);
-    double a0 = 0.0, a1 = 0.0;
-    int k = 0;
-    for (; k + 4 <= W; k += 4) {
-      const double v0 = __ldcs(v + 32 * k), v1 = __ldcs(v + 32 * (k + 1)), v2 = __ldcs(v + 32 * (k + 2)),
-                   v3 = __ldcs(v + 32 * (k + 3));
-      const unsigned j0 = __ldcs(ix + 32 * k), j1 = __ldcs(ix + 32 * (k + 1)), j2 = __ldcs(ix + 32 * (k + 2)),
-                     j3 = __ldcs(ix + 32 * (k + 3));
-      a0 += v0 * smp[j0];
-      a1 += v1 * smp[j1];
-      a0 += v2 * smp[j2];
-      a1 += v3 * smp[j3];
+  constexpr int B = kGSlabBatch;
+  for (int k = 0; k < W; k += B) {
+    double a[B][DIM];
+    unsigned j[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      j[u] = k + u < W ? __ldcs(ix + 32 * (k + u)) : 0u;
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) a[u][c] = k + u < W ? __ldcs(v + 32 * ((k + u) * DIM + c)) : 0.0;
     }
-    for (; k < W; ++k) a0 += __ldcs(v + 32 * k) * smp[__ldcs(ix + 32 * k)];
-    smo[__ldg(G.perm + (size_t)DIM * r0 + i)] = a0 + a1;
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const double p = smp[j[u]];
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) acc[c] += a[u][c] * p;
+    }
+  }
+  if ((uint32_t)t < nr) {
+    const uint32_t a = __ldg(G.perm + r0 + t);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) smo[DIM * a + c] = acc[c];
   }
   __syncthreads();
 }

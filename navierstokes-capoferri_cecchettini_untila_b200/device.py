@@ -33,7 +33,7 @@ class DeviceError(RuntimeError):
 def device_lib():
     global _lib
     if _lib is None:
-        path = os.path.join(_HERE, "libnsb.so")
+        path = os.environ.get("NSB_LIBNSB") or os.path.join(_HERE, "libnsb.so")  # override: A/B experiments only
         if not os.path.exists(path):
             raise DeviceError("libnsb.so is not built (run `make cuda`); there is no CPU fallback")
         L = C.CDLL(path, mode=C.RTLD_GLOBAL)
