@@ -90,7 +90,8 @@ int nsb_set_inner(nsb_ctx *ctx, int sweeps_F, double eig_ratio_F, int sweeps_S, 
 /* Solver for the Schur block S inside aSIMPLE.  mode 0: the single-level
  * Chebyshev-Jacobi polynomial configured by nsb_set_inner.  mode 1 (default):
  * one V-cycle over an aggregation hierarchy whose smoother is the same
- * Chebyshev-Jacobi sweep (smoother_sweeps per side, default 2;
+ * Chebyshev-Jacobi sweep (smoother_sweeps per side, default 1 -- measured on B200 at 9.7 M DoFs:
+ * 485 ms/step with 1, 514 with 2, 564 with 3;
  * strength-of-connection threshold theta, default 0.08; coarse-correction
  * scaling omega, default 1.5; `cycles` V-cycles per application, default 1).
  * Arguments <= 0 keep the defaults. */

@@ -79,7 +79,7 @@ struct nsb_ctx {
   cudaGraph_t prec_graph = nullptr;
   cudaGraphExec_t prec_exec = nullptr;
   int64_t prec_graph_kernels = 0;
-  bool use_graph = true, capturing = false;
+  bool use_graph = true, capturing = false, nccl_warm = false;
   // Krylov work space
   DevBuf<double> V, tmpN, hdev, partials, coef;
   DevBuf<unsigned> counter;
@@ -108,7 +108,7 @@ struct nsb_ctx {
   ncclComm_t comm = nullptr;
   DevBuf<double> a10t;  // A10^T values on the pattern of A01
   // ---- Schur solve: 0 = single-level Chebyshev polynomial, 1 = multilevel V-cycle (amg.cuh) ----
-  int schur_mode = 1, amg_nu = 2, amg_max_agg = 8, amg_cycles = 1, amg_coarse_sweeps = 16;
+  int schur_mode = 1, amg_nu = 1, amg_max_agg = 8, amg_cycles = 1, amg_coarse_sweeps = 16;
   double amg_theta = 0.08, amg_omega = 1.5, amg_smooth_ratio = 4.0, amg_coarse_ratio = 60.0;
   std::vector<std::unique_ptr<AmgLevel>> amg;
   bool amg_built = false;
@@ -948,7 +948,16 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
 // pz = P^-1 tmpN, as a CUDA graph captured once per time step (the coefficients of the sweeps change with
 // lambda_max and the polynomial degree, so the graph is re-captured and the executable updated in place).
 void prec_capture(nsb_ctx *c) {
-  const bool want = c->use_graph && c->prec == NSB_PREC_ASIMPLE && (c->nranks == 1 || std::getenv("NSB_GRAPH_NCCL"));
+  // On several GPUs the graph contains the NCCL halo / broadcast kernels as well (NSB_GRAPH_NCCL=0 keeps them out
+  // by launching the preconditioner directly): ~30 latency-bound launches per application become one.
+  const char *gn = std::getenv("NSB_GRAPH_NCCL");
+  const bool want = c->use_graph && c->prec == NSB_PREC_ASIMPLE && (c->nranks == 1 || !gn || std::atoi(gn) != 0);
+  if (want && c->nranks > 1 && !c->nccl_warm) {
+    // every collective of the sequence runs once outside a capture first (NCCL sets up its connections lazily)
+    prec_apply(c, c->tmpN.p, c->pz.p);
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+    c->nccl_warm = true;
+  }
   if (!want) {
     if (c->prec_exec) cudaGraphExecDestroy(c->prec_exec);
     c->prec_exec = nullptr;
