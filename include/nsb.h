@@ -46,8 +46,9 @@ enum { NSB_A00 = 0, NSB_A01 = 1, NSB_A10 = 2, NSB_S = 3 };
 enum { NSB_QUAD_DEALII93 = 0, NSB_QUAD_DEALII95 = 1 };
 /* treatment of the diagonal of constrained rows in apply_boundary_values */
 enum { NSB_BCDIAG_KEEP = 0, NSB_BCDIAG_FIRST = 1 };
-/* preconditioner selection (reference NavierStokes.cpp:352-373) */
-enum { NSB_PREC_ASIMPLE = 0, NSB_PREC_IDENTITY = 1 };
+/* preconditioner selection (reference NavierStokes.cpp:352-373): PreconditionASIMPLE (:934-995, the one the
+ * reference enables), PreconditionIdentity (NavierStokes.hpp:274-287), PreconditionAYosida (:998-1051) */
+enum { NSB_PREC_ASIMPLE = 0, NSB_PREC_IDENTITY = 1, NSB_PREC_AYOSIDA = 2 };
 
 const char *nsb_last_error(const nsb_ctx *ctx);
 /* Number of CUDA devices visible (0 when none / no driver). */
@@ -119,6 +120,9 @@ int nsb_get_matrix_values(nsb_ctx *ctx, int block, double *vals_host);
 int nsb_get_pattern(nsb_ctx *ctx, int block, int64_t *rowptr_host, uint32_t *colind_host);
 int64_t nsb_nnz(const nsb_ctx *ctx, int block);
 int nsb_get_rhs(nsb_ctx *ctx, double *rhs_host);
+/* deltat_lumped_mass_inv of the reference (NavierStokes.cpp:232-236, 252, 284-290), velocity block: n_u values
+ * deltat / sum_cells sum_q sum_j |phi_j . phi_i JxW| (the pressure block of the reference vector is deltat/0). */
+int nsb_get_lumped_mass_inv(nsb_ctx *ctx, double *out_host);
 /* y = A x with host vectors (n_u+n_p). */
 int nsb_vmult(nsb_ctx *ctx, const double *x_host, double *y_host);
 /* Device-resident micro-benchmarks: run `reps` launches and return the mean

@@ -360,9 +360,12 @@ __global__ void apply_dirichlet_kernel(int64_t n_bc_nodes, const uint32_t *__res
   }
 }
 
-// diagonal of the velocity mass matrix, M_AA = sum_cells |J| M^(a,a) (geometry only; computed once).
-// Used to choose the degree of the Chebyshev polynomial for F (see auto_inner in nsb_capi.cu).
-template <int DIM>
+// LUMPED == false: diagonal of the velocity mass matrix, M_AA = sum_cells |J| M^(a,a) (used to choose the
+// degree of the Chebyshev polynomial for F, see auto_inner in nsb_capi.cu).
+// LUMPED == true: the reference's lumped mass sum_cells sum_q sum_b |phi_a phi_b JxW| per node
+// (NavierStokes.cpp:232-236, 252, 284; consumed by PreconditionAYosida as deltat / lumped).
+// Geometry only; computed once.
+template <int DIM, bool LUMPED>
 __global__ void mass_diag_kernel(int64_t n_cells, const double *__restrict__ xyz,
                                  const uint32_t *__restrict__ cell_verts, const uint32_t *__restrict__ cell_nodes,
                                  uint32_t n_own_nodes, const FeTables *__restrict__ fe, double *mdiag) {
@@ -384,7 +387,7 @@ __global__ void mass_diag_kernel(int64_t n_cells, const double *__restrict__ xyz
   }
   for (int a = 0; a < NN; ++a) {
     const uint32_t node = cell_nodes[cell * NN + a];
-    if (node < n_own_nodes) atomicAdd(mdiag + node, fabs(det) * fe->mhat[a][a]);
+    if (node < n_own_nodes) atomicAdd(mdiag + node, fabs(det) * (LUMPED ? fe->labs[a] : fe->mhat[a][a]));
   }
 }
 

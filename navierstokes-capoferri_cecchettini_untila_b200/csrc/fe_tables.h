@@ -22,6 +22,7 @@ struct FeTables {
   double mhat[kMaxNN][kMaxNN];         // sum_q w phi_a phi_b
   double dhat[kMaxNN][kMaxNV][3];      // sum_q w d_d(phi_a) psi_k
   double wface[7];                     // face weights, normalised to sum 1
+  double labs[kMaxNN];                 // sum_q w |phi_a| sum_b |phi_b|  (lumped mass of reference :232-236)
 };
 
 namespace fe_detail {
@@ -134,6 +135,12 @@ inline bool fill_fe_tables(int dim, int rule, FeTables &T) {
       double s = 0;
       for (int q = 0; q < T.nq; ++q) s += T.w[q] * T.phi[q][a] * T.phi[q][b];
       T.mhat[a][b] = s;
+    }
+    {
+      double s = 0;  // the absolute value is taken per (q, j) term, as in the reference
+      for (int q = 0; q < T.nq; ++q)
+        for (int b = 0; b < T.nn; ++b) s += std::fabs(T.w[q] * T.phi[q][a] * T.phi[q][b]);
+      T.labs[a] = s;
     }
     for (int k = 0; k < T.nv; ++k)
       for (int d = 0; d < dim; ++d) {

@@ -67,6 +67,7 @@ struct nsb_ctx {
   int kF = 3, kS = 20;           // values in effect for the current step
   double rF = 6.0, rS = 300.0;
   DevBuf<double> mdiag;          // diagonal of the velocity mass matrix (owned nodes)
+  DevBuf<double> lumped, dtm;    // aYosida: lumped mass per owned node, deltat / lumped per owned velocity dof
   SlabDev fslab;                 // F_s in slab (windowed sliced-ELL) form: what the solver kernels stream
   GSlabDev gslab;                // A01 in the same slabs
   size_t fslab_smem = 0, fapply_smem = 0, gapply_smem = 0;  // dynamic shared memory of the slab kernels
@@ -304,7 +305,7 @@ void fs_apply(nsb_ctx *c, int mode, const double *xu, const double *xp, const do
 #undef NSB_FS_CASE
 }
 
-// y = w - d .* (A01 xp) over the owned velocity rows
+// y = w - d .* (A01 xp) over the owned velocity rows; w == nullptr: y = A01 xp
 void g_apply(nsb_ctx *c, const double *xp, const double *w, const double *d, double *y) {
   const unsigned grid = (unsigned)c->fslab.n_slabs;
   if (c->dim == 2)
@@ -442,6 +443,13 @@ double norm2_host(nsb_ctx *c, const double *v, Part part) {
   NSB_CUDA(cudaMemcpyAsync(&h, c->hdev.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   NSB_CUDA(cudaStreamSynchronize(c->stream));
   return std::sqrt(h);
+}
+
+// dtm[i] = deltat / lumped[i / dim]   (deltat_lumped_mass_inv of the reference, velocity block)
+__global__ void dt_over_lumped_kernel(int64_t n, int dim, double dt, const double *__restrict__ lumped,
+                                      double *__restrict__ dtm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dtm[i] = dt / lumped[i / dim];
 }
 
 __global__ void eig_seed_kernel(int64_t n, double *v) {
@@ -660,10 +668,10 @@ void finalize_setup(nsb_ctx *c) {
     c->send_buf.alloc((size_t)c->send_ptr.back() * c->dim, &c->dev_bytes);
   build_fslab(c);
   if (c->dim == 2)
-    NSB_LAUNCH(c, mass_diag_kernel<2>, blocks_for(c->n_cells), 256, c->n_cells, c->xyz.p, c->cell_verts.p,
+    NSB_LAUNCH(c, (mass_diag_kernel<2, false>), blocks_for(c->n_cells), 256, c->n_cells, c->xyz.p, c->cell_verts.p,
                c->cell_nodes.p, c->n_own_nodes, c->fe.p, c->mdiag.p);
   else
-    NSB_LAUNCH(c, mass_diag_kernel<3>, blocks_for(c->n_cells), 256, c->n_cells, c->xyz.p, c->cell_verts.p,
+    NSB_LAUNCH(c, (mass_diag_kernel<3, false>), blocks_for(c->n_cells), 256, c->n_cells, c->xyz.p, c->cell_verts.p,
                c->cell_nodes.p, c->n_own_nodes, c->fe.p, c->mdiag.p);
   NSB_LAUNCH(c, eig_seed_kernel, blocks_for(c->n_u), 256, (int64_t)c->n_u, c->eig_u.p);
   NSB_LAUNCH(c, eig_seed_kernel, blocks_for(c->n_p), 256, (int64_t)c->n_p, c->eig_p.p);
@@ -887,16 +895,36 @@ void auto_inner(nsb_ctx *c) {
   }
 }
 
-// PreconditionASIMPLE::initialize, reference :934-963
+// lumped velocity mass of the reference (:232-236), geometry only: computed at first use
+void ensure_lumped(nsb_ctx *c) {
+  if (c->lumped.p) return;
+  c->lumped.alloc((size_t)c->n_own_nodes, &c->dev_bytes);
+  c->lumped.zero(c->stream);
+  c->dtm.alloc((size_t)c->n_u, &c->dev_bytes);
+  if (c->dim == 2)
+    NSB_LAUNCH(c, (mass_diag_kernel<2, true>), blocks_for(c->n_cells), 256, c->n_cells, c->xyz.p, c->cell_verts.p,
+               c->cell_nodes.p, c->n_own_nodes, c->fe.p, c->lumped.p);
+  else
+    NSB_LAUNCH(c, (mass_diag_kernel<3, true>), blocks_for(c->n_cells), 256, c->n_cells, c->xyz.p, c->cell_verts.p,
+               c->cell_nodes.p, c->n_own_nodes, c->fe.p, c->lumped.p);
+}
+
+// PreconditionASIMPLE::initialize (reference :934-963) / PreconditionAYosida::initialize (:998-1020)
 void prec_init(nsb_ctx *c) {
   auto_inner(c);
   NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_u), 256, (int64_t)c->n_u, c->dim, c->fs.val.p, c->diagF.p,
              c->di.p);
   NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_own_nodes), 256, (int64_t)c->n_own_nodes, 1, c->fs.val.p, c->diagF.p,
              c->din.p);
-  if (c->prec != NSB_PREC_ASIMPLE) return;
+  if (c->prec == NSB_PREC_IDENTITY) return;
+  const double *sdiag = c->di.p;  // aSIMPLE: S = B diag(F)^-1 Bt (reference :951-956)
+  if (c->prec == NSB_PREC_AYOSIDA) {  // aYosida: S = B (deltat M_l^-1) Bt (reference :1012)
+    ensure_lumped(c);
+    NSB_LAUNCH(c, dt_over_lumped_kernel, blocks_for(c->n_u), 256, (int64_t)c->n_u, c->dim, c->dt, c->lumped.p, c->dtm.p);
+    sdiag = c->dtm.p;
+  }
   c->s.val.zero(c->stream);
-  NSB_LAUNCH(c, schur_outer_kernel, blocks_for((int64_t)c->n_u * 32), 256, c->a01.view(), c->a10t.p, c->di.p,
+  NSB_LAUNCH(c, schur_outer_kernel, blocks_for((int64_t)c->n_u * 32), 256, c->a01.view(), c->a10t.p, sdiag,
              c->s.view());
   allreduce_sum(c, c->s.val.p, (size_t)c->s.nnz);
   NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_p), 256, (int64_t)c->n_p, 1, c->s.val.p, c->diagS.p, c->dis.p);
@@ -910,6 +938,39 @@ void prec_init(nsb_ctx *c) {
   c->eig_warm = true;
 }
 
+// S^-1 b on the replicated pressure vectors: one (or amg_cycles) V-cycle(s), or the single-level polynomial
+const double *schur_solve(nsb_ctx *c, const double *b) {
+  const int64_t np = c->n_p;
+  if (c->schur_mode != 1) {
+    cheb_solve(c, &c->s, c->dis.p, b, c->chz_p2.p, c->chz_p.p, c->chd_p.p, c->kS, c->lamS, c->rS);
+    return c->chz_p2.p;
+  }
+  const double *d1 = amg_vcycle(c, 0, b);
+  for (int cyc = 1; cyc < c->amg_cycles; ++cyc) {  // further cycles on the residual equation
+    spmv(c, c->s, 1, d1, b, nullptr, c->chz_p.p);
+    NSB_CUDA(cudaMemcpyAsync(c->chz_p2.p, d1, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    const double *e = amg_vcycle(c, 0, c->chz_p.p);
+    NSB_LAUNCH(c, axpby_kernel, kRedBlocks, 256, np, 1.0, e, 1.0, c->chz_p2.p);
+    d1 = c->chz_p2.p;
+  }
+  return d1;
+}
+
+// PreconditionAYosida::vmult, reference :1024-1051, inner solves as in prec_apply:
+//   vec0 ~= F^-1 src0;  vec1 = B vec0 - src1;  dst1 ~= S^-1 vec1;  dst0 = vec0 - F^-1 (Bt dst1)
+void prec_apply_yosida(nsb_ctx *c, const double *src, double *dst) {
+  const int64_t np = c->n_p;
+  cheb_solve_F(c, src, c->vec0.p, c->kF, c->lamF, c->rF);                                          // :1035-1037
+  halo_exchange(c, c->vec0.p);
+  spmv(c, c->a10, 1, c->vec0.p, src + c->n_uloc + c->p_begin, nullptr, c->vec1.p + c->p_begin);   // src1 - B vec0
+  allgather_p(c, c->vec1.p);
+  const double *d1 = schur_solve(c, c->vec1.p);                                                     // :1042-1044
+  NSB_LAUNCH(c, scale_kernel, blocks_for(np), 256, np, -1.0, d1, dst + c->n_uloc);                  // sign of :1039
+  g_apply(c, dst + c->n_uloc, nullptr, nullptr, c->eig_w.p);                                        // Bt dst1, :1047
+  cheb_solve_F(c, c->eig_w.p, dst, c->kF, c->lamF, c->rF);                                          // :1048
+  NSB_LAUNCH(c, axpby_kernel, kRedBlocks, 256, (int64_t)c->n_u, 1.0, c->vec0.p, -1.0, dst);         // :1049
+}
+
 // PreconditionASIMPLE::vmult, reference :966-995, with the two inner solves
 // replaced by Chebyshev-Jacobi polynomials of fixed degree (a linear,
 // stationary operator: no stale initial guesses).
@@ -919,6 +980,10 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
     NSB_CUDA(cudaMemcpyAsync(dst, src, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return;
   }
+  if (c->prec == NSB_PREC_AYOSIDA) {
+    prec_apply_yosida(c, src, dst);
+    return;
+  }
   // vec0 ~= F^-1 src0                                   (:978-981)
   cheb_solve_F(c, src, c->vec0.p, c->kF, c->lamF, c->rF);
   // vec1 = src1 - B vec0                                 (:982-983)
@@ -926,20 +991,7 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
   spmv(c, c->a10, 1, c->vec0.p, src + c->n_uloc + c->p_begin, nullptr, c->vec1.p + c->p_begin);
   allgather_p(c, c->vec1.p);
   // dst1 ~= S^-1 vec1, then dst1 *= -1/alpha             (:986-990)
-  const double *d1;
-  if (c->schur_mode == 1) {
-    d1 = amg_vcycle(c, 0, c->vec1.p);
-    for (int cyc = 1; cyc < c->amg_cycles; ++cyc) {  // further cycles on the residual equation
-      spmv(c, c->s, 1, d1, c->vec1.p, nullptr, c->chz_p.p);
-      NSB_CUDA(cudaMemcpyAsync(c->chz_p2.p, d1, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-      const double *e = amg_vcycle(c, 0, c->chz_p.p);
-      NSB_LAUNCH(c, axpby_kernel, kRedBlocks, 256, np, 1.0, e, 1.0, c->chz_p2.p);
-      d1 = c->chz_p2.p;
-    }
-  } else {
-    cheb_solve(c, &c->s, c->dis.p, c->vec1.p, c->chz_p2.p, c->chz_p.p, c->chd_p.p, c->kS, c->lamS, c->rS);
-    d1 = c->chz_p2.p;
-  }
+  const double *d1 = schur_solve(c, c->vec1.p);
   NSB_LAUNCH(c, scale_kernel, blocks_for(np), 256, np, -1.0 / c->alpha, d1, dst + c->n_uloc);
   // dst0 = vec0 - Di .* (Bt dst1)                        (:992-994)
   g_apply(c, dst + c->n_uloc, c->vec0.p, c->di.p, dst);
@@ -951,7 +1003,7 @@ void prec_capture(nsb_ctx *c) {
   // On several GPUs the graph contains the NCCL halo / broadcast kernels as well (NSB_GRAPH_NCCL=0 keeps them out
   // by launching the preconditioner directly): ~30 latency-bound launches per application become one.
   const char *gn = std::getenv("NSB_GRAPH_NCCL");
-  const bool want = c->use_graph && c->prec == NSB_PREC_ASIMPLE && (c->nranks == 1 || !gn || std::atoi(gn) != 0);
+  const bool want = c->use_graph && c->prec != NSB_PREC_IDENTITY && (c->nranks == 1 || !gn || std::atoi(gn) != 0);
   if (want && c->nranks > 1 && !c->nccl_warm) {
     // every collective of the sequence runs once outside a capture first (NCCL sets up its connections lazily)
     prec_apply(c, c->tmpN.p, c->pz.p);
@@ -1345,7 +1397,9 @@ int nsb_set_bc_diag_mode(nsb_ctx *c, int mode) {
 int nsb_set_solver(nsb_ctx *c, double gmres_rtol, int restart, int max_it, double alpha, int preconditioner) {
   return guarded(c, [&] {
     if (restart < 1 || restart > kMaxDots - 2) throw ArgError("nsb_set_solver: restart out of range [1,62]");
-    if (preconditioner != NSB_PREC_ASIMPLE && preconditioner != NSB_PREC_IDENTITY) throw ArgError("bad preconditioner");
+    if (preconditioner != NSB_PREC_ASIMPLE && preconditioner != NSB_PREC_IDENTITY && preconditioner != NSB_PREC_AYOSIDA)
+      throw ArgError("bad preconditioner");
+    if (preconditioner != c->prec) c->amg_built = false;  // the hierarchy is built from the first S of a kind
     c->rtol = gmres_rtol;
     c->restart = restart;
     c->max_it = max_it;
@@ -1532,6 +1586,14 @@ int64_t nsb_nnz(const nsb_ctx *c, int block) {
   if (block == NSB_A00) return c->fs.have ? c->fs.nnz * c->dim * c->dim : -1;
   const CsrDev *A = block_of(const_cast<nsb_ctx *>(c), block);
   return A && A->have ? A->nnz : -1;
+}
+int nsb_get_lumped_mass_inv(nsb_ctx *c, double *out) {
+  return guarded(c, [&] {
+    finalize_setup(c);
+    ensure_lumped(c);
+    NSB_LAUNCH(c, dt_over_lumped_kernel, blocks_for(c->n_u), 256, (int64_t)c->n_u, c->dim, c->dt, c->lumped.p, c->dtm.p);
+    c->dtm.download(out, c->stream);
+  });
 }
 int nsb_get_rhs(nsb_ctx *c, double *rhs) {
   return guarded(c, [&] {

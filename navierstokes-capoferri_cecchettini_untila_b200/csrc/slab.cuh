@@ -593,7 +593,8 @@ __global__ void __launch_bounds__(kSlabThreads) fs_slab_apply_kernel(SlabView S,
   }
 }
 
-// y = w - d .* (A01 xp)   (dst0 = vec0 - Di .* (Bt dst1), reference :992-994) over the velocity rows
+// y = w - d .* (A01 xp)   (dst0 = vec0 - Di .* (Bt dst1), reference :992-994) over the velocity rows;
+// w == nullptr: y = A01 xp   (Bt dst1 of PreconditionAYosida::vmult, reference :1047)
 template <int DIM>
 __global__ void __launch_bounds__(kSlabThreads) g_slab_apply_kernel(SlabView S, GSlabView G,
                                                                     const double *__restrict__ xp,
@@ -607,7 +608,7 @@ __global__ void __launch_bounds__(kSlabThreads) g_slab_apply_kernel(SlabView S, 
   slab_g_product<DIM>(G, s, r0, nr, xp, smp, smo);
   for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
     const int64_t g = (int64_t)DIM * r0 + i;
-    y[g] = w[g] - d[g] * smo[i];
+    y[g] = w != nullptr ? w[g] - d[g] * smo[i] : smo[i];
   }
 }
 

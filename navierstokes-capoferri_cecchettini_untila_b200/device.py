@@ -11,7 +11,7 @@ _lib = None
 
 A00, A01, A10, S = 0, 1, 2, 3
 QUAD_DEALII93, QUAD_DEALII95 = 0, 1
-PREC_ASIMPLE, PREC_IDENTITY = 0, 1
+PREC_ASIMPLE, PREC_IDENTITY, PREC_AYOSIDA = 0, 1, 2
 
 # every symbol include/nsb.h declares (tests check the .so exports them all)
 SYMBOLS = [
@@ -22,7 +22,7 @@ SYMBOLS = [
     "nsb_compute_forces", "nsb_get_matrix_values", "nsb_get_pattern", "nsb_nnz", "nsb_get_rhs", "nsb_vmult",
     "nsb_bench_kernel", "nsb_launch_count", "nsb_timers", "nsb_info", "nsb_alloc_pinned", "nsb_free_pinned",
     "nsb_comm_unique_id", "nsb_comm_init", "nsb_set_local_dofs", "nsb_set_halo", "nsb_set_schur_solver", "nsb_gather_velocity",
-    "nsb_slab_host_check", "nsb_gslab_host_check",
+    "nsb_slab_host_check", "nsb_gslab_host_check", "nsb_get_lumped_mass_inv",
 ]
 
 
@@ -67,6 +67,7 @@ def device_lib():
         L.nsb_nnz.argtypes = [p, C.c_int]
         L.nsb_nnz.restype = C.c_int64
         L.nsb_get_rhs.argtypes = [p, f64p]
+        L.nsb_get_lumped_mass_inv.argtypes = [p, f64p]
         L.nsb_vmult.argtypes = [p, f64p, f64p]
         L.nsb_bench_kernel.argtypes = [p, C.c_int, C.c_int, f64p]
         L.nsb_launch_count.argtypes = [p]
@@ -303,6 +304,12 @@ class Device:
     def rhs(self):
         out = np.empty(self.N, np.float64)
         self._chk(self.L.nsb_get_rhs(self.h, _p(out, C.c_double)))
+        return out
+
+    def lumped_mass_inv(self, n_u):
+        """deltat_lumped_mass_inv of the reference, velocity block (n_u values)."""
+        out = np.empty(n_u, np.float64)
+        self._chk(self.L.nsb_get_lumped_mass_inv(self.h, _p(out, C.c_double)))
         return out
 
     def vmult(self, x):

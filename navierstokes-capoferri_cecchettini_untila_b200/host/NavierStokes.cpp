@@ -17,6 +17,13 @@
 #include "distribute.hpp"
 #include "problem.hpp"
 
+// Preconditioner of solve_time_step.  The reference selects it by (un)commenting blocks of
+// NavierStokes.cpp:352-373; here it is a compile-time switch: NSB_PREC_ASIMPLE (the block the reference leaves
+// enabled, :355-361), NSB_PREC_AYOSIDA (:364-373) or NSB_PREC_IDENTITY (:352).
+#ifndef NS_PRECONDITIONER
+#define NS_PRECONDITIONER NSB_PREC_ASIMPLE
+#endif
+
 namespace {
 unsigned int env_uint(const char *name, unsigned int dflt) {
   const char *v = std::getenv(name);
@@ -111,7 +118,7 @@ void NavierStokes::setup() {
                             problem->ff.measure.data()),
         "nsb_set_force_faces");
   check(nsb_set_params(ctx, deltat, nu), "nsb_set_params");
-  check(nsb_set_solver(ctx, opt_rtol, opt_restart, opt_max_it, 0.5, NSB_PREC_ASIMPLE), "nsb_set_solver");
+  check(nsb_set_solver(ctx, opt_rtol, opt_restart, opt_max_it, 0.5, NS_PRECONDITIONER), "nsb_set_solver");
   if (opt_sweeps_F > 0 && opt_sweeps_S > 0)
     check(nsb_set_inner(ctx, opt_sweeps_F, 2.5 * opt_sweeps_F, opt_sweeps_S, 0.45 * opt_sweeps_S * opt_sweeps_S),
           "nsb_set_inner");
@@ -130,7 +137,7 @@ void NavierStokes::set_solver_options(double gmres_rtol, int restart, int max_it
   opt_sweeps_F = sweeps_F;
   opt_sweeps_S = sweeps_S;
   if (ctx) {
-    check(nsb_set_solver(ctx, opt_rtol, opt_restart, opt_max_it, 0.5, NSB_PREC_ASIMPLE), "nsb_set_solver");
+    check(nsb_set_solver(ctx, opt_rtol, opt_restart, opt_max_it, 0.5, NS_PRECONDITIONER), "nsb_set_solver");
     if (sweeps_F > 0 && sweeps_S > 0)
       check(nsb_set_inner(ctx, sweeps_F, 2.5 * sweeps_F, sweeps_S, 0.45 * sweeps_S * sweeps_S), "nsb_set_inner");
   }
@@ -215,7 +222,7 @@ void NavierStokes::setup_distributed() {
   check(nsb_set_force_faces(ctx, (int64_t)L.ff_cell.size(), L.ff_cell.data(), L.ff_normal.data(), L.ff_measure.data()),
         "nsb_set_force_faces");
   check(nsb_set_params(ctx, deltat, nu), "nsb_set_params");
-  check(nsb_set_solver(ctx, opt_rtol, opt_restart, opt_max_it, 0.5, NSB_PREC_ASIMPLE), "nsb_set_solver");
+  check(nsb_set_solver(ctx, opt_rtol, opt_restart, opt_max_it, 0.5, NS_PRECONDITIONER), "nsb_set_solver");
   refresh_dirichlet(0.0);
   check(nsb_finalize_setup(ctx), "nsb_finalize_setup");
   local_vec.assign((size_t)dim * (L.n_own + L.n_ghost) + L.n_p, 0.0);

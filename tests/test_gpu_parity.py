@@ -176,3 +176,46 @@ def test_errors_are_reported_not_thrown(pkg):
     scr[0], scr[1] = scr[1], scr[0]  # break the dim*node+c structure
     rc = L.nsb_set_dofs(dev.h, prob.sizes()["n_u"], prob.sizes()["n_p"], scr.ctypes.data_as(C.POINTER(C.c_uint32)))
     assert rc == -3
+
+
+@pytest.mark.parametrize("key", ["2d-cylinder", "3d-cylinder"])
+def test_lumped_mass_inverse_matches_oracle(pkg, oracle_mod, key):
+    """deltat_lumped_mass_inv (reference :232-236, 252, 284-290), velocity block."""
+    prob, orc, dim, nu, um = make_case(pkg, oracle_mod, key)
+    dev = _device(pkg, prob, dim, nu)
+    orc.assemble(0.01)
+    dev.assemble(0.01)
+    ref = orc.lumped()[: orc.n_u]
+    got = dev.lumped_mass_inv(orc.n_u)
+    assert np.all(np.isfinite(ref)) and _rel(got, ref) < 1e-12
+
+
+@pytest.mark.parametrize("key", ["2d-cylinder", "3d-cylinder"])
+def test_yosida_preconditioner(pkg, oracle_mod, key):
+    """PreconditionAYosida (reference :998-1051): S = B (deltat M_l^-1) Bt entry-wise against the
+    product of the oracle's blocks, and the solution of the preconditioned solve against the oracle's
+    (aSIMPLE) solution with both run to 1e-12 (a preconditioner does not change the solution)."""
+    import scipy.sparse as sp
+    prob, orc, dim, nu, um = make_case(pkg, oracle_mod, key)
+    dev = _device(pkg, prob, dim, nu)
+    orc.set_solver(1e-12, 30, 10000, 1e-10)
+    dev.set_solver(gmres_rtol=1e-12, restart=60, preconditioner=pkg.device.PREC_AYOSIDA)
+    x = seeded_state(orc)
+    orc.set_solution(x)
+    dev.set_solution(x)
+    orc.assemble(0.01)
+    dev.assemble(0.01)
+    rc, it_o, _, _ = orc.solve_time_step()
+    it_d, _, _ = dev.solve_time_step()
+    assert rc == 0 and 0 < it_d < 400
+    xo, xd = orc.solution(), dev.solution()
+    assert np.linalg.norm(xd - xo) / np.linalg.norm(xo) < 1e-8
+    n_u, n_p = orc.n_u, orc.n_p
+    rp01, ci01 = orc.pattern("a01")
+    rp10, ci10 = orc.pattern("a10")
+    Bt = sp.csr_matrix((orc.values("a01"), ci01.astype(np.int64), rp01), shape=(n_u, n_p))
+    B = sp.csr_matrix((orc.values("a10"), ci10.astype(np.int64), rp10), shape=(n_p, n_u))
+    S_ref = (B @ sp.diags(orc.lumped()[:n_u]) @ Bt).tocsr()
+    rp_s, ci_s = dev.pattern(pkg.device.S)
+    S_dev = sp.csr_matrix((dev.values(pkg.device.S), ci_s.astype(np.int64), rp_s), shape=(n_p, n_p))
+    assert abs(S_dev - S_ref).max() < ENTRY_TOL * abs(S_ref).max()
