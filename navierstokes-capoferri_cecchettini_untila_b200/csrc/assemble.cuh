@@ -33,7 +33,6 @@ struct AsmArgs {
   const uint16_t *slot10;       // n_cells*NV*NN
   const int64_t *nptr, *rowptr01, *rowptr10;  // nptr: node-level row offsets of F_s
   double *fs_val, *val01, *val10;
-  double *val10t;  // A10 transposed on the pattern of A01 (not touched by the Dirichlet rows); feeds S
   // ownership (multi-GPU): rows of local nodes >= n_own_nodes and of pressure
   // vertices outside [p_begin, p_begin + n_p_own) belong to another rank
   uint32_t n_own_nodes, p_begin, n_p_own;
@@ -161,24 +160,28 @@ __global__ void expand_node_pattern_kernel(int64_t n_nodes, const int64_t *__res
 // ---------------------------------------------------------------------------
 constexpr int kAsmWarps = 8;
 
-template <int DIM, int NQ>
+// The scalar velocity block needs no quadrature loop at run time.  With G_a = J^{-T} grad_hat(phi_a) and
+// u_q = sum_n phi_n(q) U_n (reference :175, :197-208):
+//   sum_q w_q G_a.G_b               = sum_{d,e} Q_de khat[de](a,b),        Q = J^{-1} J^{-T}
+//   sum_q w_q phi_a (u_q . G_b)     = sum_{n,d} chat[nd](a,b) Uh_nd,       Uh_nd = sum_c J^{-1}[d][c] U_n[c]
+// khat / chat are contractions of the SAME quadrature table the reference uses (fe_tables.h), so its
+// under-integration is reproduced; 9 + 30 conflict-free shared-memory reads per (a,b) pair replace the
+// 14 x 12 of the quadrature loop, which made the kernel shared-memory-bandwidth bound (13 ms at 2.25 M cells).
+template <int DIM>
 __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs A) {
-  constexpr int NV = DIM + 1, NN = DIM == 2 ? 6 : 10;
-  __shared__ double s_w[NQ], s_phi[NQ][NN], s_dphi[NQ][NN][DIM], s_mhat[NN][NN], s_dhat[NN][NV][DIM];
-  __shared__ double s_G[kAsmWarps][NQ][NN][DIM];
+  constexpr int NV = DIM + 1, NN = DIM == 2 ? 6 : 10, NP = NN * NN, ND = NN * DIM;
+  __shared__ double s_mhat[NN][NN], s_dhat[NN][NV][DIM], s_khat[DIM * DIM][NP], s_chat[ND][NP];
   __shared__ double s_U[kAsmWarps][NN][DIM];
-  __shared__ double s_uq[kAsmWarps][NQ][DIM];
+  __shared__ double s_Uh[kAsmWarps][ND];
   __shared__ int64_t s_rp00[kAsmWarps][NN], s_rp01[kAsmWarps][NN], s_rp10[kAsmWarps][NV];
   __shared__ int s_len01[kAsmWarps][NN];
   __shared__ uint32_t s_node[kAsmWarps][NN];
 
-  for (int i = threadIdx.x; i < NQ; i += blockDim.x) s_w[i] = A.fe->w[i];
-  for (int i = threadIdx.x; i < NQ * NN; i += blockDim.x) s_phi[i / NN][i % NN] = A.fe->phi[i / NN][i % NN];
-  for (int i = threadIdx.x; i < NQ * NN * DIM; i += blockDim.x)
-    s_dphi[i / (NN * DIM)][(i / DIM) % NN][i % DIM] = A.fe->dphi[i / (NN * DIM)][(i / DIM) % NN][i % DIM];
   for (int i = threadIdx.x; i < NN * NN; i += blockDim.x) s_mhat[i / NN][i % NN] = A.fe->mhat[i / NN][i % NN];
   for (int i = threadIdx.x; i < NN * NV * DIM; i += blockDim.x)
     s_dhat[i / (NV * DIM)][(i / DIM) % NV][i % DIM] = A.fe->dhat[i / (NV * DIM)][(i / DIM) % NV][i % DIM];
+  for (int i = threadIdx.x; i < DIM * DIM * NP; i += blockDim.x) s_khat[i / NP][i % NP] = A.fe->khat[i / NP][i % NP];
+  for (int i = threadIdx.x; i < ND * NP; i += blockDim.x) s_chat[i / NP][i % NP] = A.fe->chat[i / NP][i % NP];
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -242,49 +245,43 @@ __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs 
       s_rp10[warp][lane - 16] = pv < A.n_p_own ? __ldg(A.rowptr10 + pv) : -1;
     }
     __syncwarp();
-    // previous-step velocity at the cell's nodes (reference :175)
-    for (int e = lane; e < NN * DIM; e += 32) {
+    // previous-step velocity at the cell's nodes (reference :175), as is and pulled back to the reference cell
+    for (int e = lane; e < ND; e += 32) {
       const int n = e / DIM, c = e % DIM;
       s_U[warp][n][c] = __ldg(A.sol + (size_t)DIM * s_node[warp][n] + c);
     }
-    // physical gradients G_a(q) = J^{-T} grad_hat phi_a(q)
-    for (int e = lane; e < NQ * NN; e += 32) {
-      const int q = e / NN, a = e % NN;
-#pragma unroll
-      for (int c = 0; c < DIM; ++c) {
-        double g = 0;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) g += Ji[d][c] * s_dphi[q][a][d];
-        s_G[warp][q][a][c] = g;
-      }
-    }
     __syncwarp();
-    for (int e = lane; e < NQ * DIM; e += 32) {
-      const int q = e / DIM, c = e % DIM;
+    for (int e = lane; e < ND; e += 32) {
+      const int n = e / DIM, d = e % DIM;
       double u = 0;
 #pragma unroll
-      for (int n = 0; n < NN; ++n) u += s_phi[q][n] * s_U[warp][n][c];
-      s_uq[warp][q][c] = u;
+      for (int c = 0; c < DIM; ++c) u += Ji[d][c] * s_U[warp][n][c];
+      s_Uh[warp][e] = u;
     }
+    double Q[DIM][DIM];  // J^{-1} J^{-T}
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+      for (int e = 0; e < DIM; ++e) {
+        double q = 0;
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) q += Ji[d][c] * Ji[e][c];
+        Q[d][e] = q;
+      }
     __syncwarp();
 
     // ---- scalar velocity block -> F_s ----
-    const uint16_t *sl00 = A.slot00 + cell * (NN * NN);
-    for (int p = lane; p < NN * NN; p += 32) {
-      const int a = p / NN, b = p % NN;
-      double acc = 0;
+    const uint16_t *sl00 = A.slot00 + cell * NP;
+    for (int p = lane; p < NP; p += 32) {
+      const int a = p / NN;
+      double stiff = 0, conv = 0;
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        double gg = 0, ug = 0;
+      for (int d = 0; d < DIM; ++d)
 #pragma unroll
-        for (int c = 0; c < DIM; ++c) {
-          const double gb = s_G[warp][q][b][c];
-          gg += s_G[warp][q][a][c] * gb;
-          ug += s_uq[warp][q][c] * gb;
-        }
-        acc += s_w[q] * (A.nu * gg + s_phi[q][a] * ug);
-      }
-      const double v = adet * (acc + s_mhat[a][b] * A.inv_dt);
+        for (int e = 0; e < DIM; ++e) stiff += Q[d][e] * s_khat[d * DIM + e][p];
+#pragma unroll
+      for (int nd = 0; nd < ND; ++nd) conv += s_chat[nd][p] * s_Uh[warp][nd];
+      const double v = adet * (A.nu * stiff + conv + s_mhat[a][p % NN] * A.inv_dt);
       if (s_rp00[warp][a] >= 0) atomicAdd(A.fs_val + s_rp00[warp][a] + sl00[p], v);
     }
     // ---- pressure-velocity coupling -> A01 and A10 (reference :222-229) ----
@@ -298,7 +295,6 @@ __global__ void __launch_bounds__(kAsmWarps * 32) assemble_cells_kernel(AsmArgs 
       if (s_rp00[warp][a] >= 0) {
         const int64_t pos = s_rp01[warp][a] + (int64_t)c * s_len01[warp][a] + sl01[a * NV + k];
         atomicAdd(A.val01 + pos, v);
-        atomicAdd(A.val10t + pos, v);
       }
       if (s_rp10[warp][k] >= 0) atomicAdd(A.val10 + s_rp10[warp][k] + (int64_t)DIM * sl10[k * NN + a] + c, v);
     }

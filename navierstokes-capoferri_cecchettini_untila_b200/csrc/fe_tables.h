@@ -23,6 +23,11 @@ struct FeTables {
   double dhat[kMaxNN][kMaxNV][3];      // sum_q w d_d(phi_a) psi_k
   double wface[7];                     // face weights, normalised to sum 1
   double labs[kMaxNN];                 // sum_q w |phi_a| sum_b |phi_b|  (lumped mass of reference :232-236)
+  // geometry-independent contractions of the stiffness and convection terms (pair p = a*nn + b):
+  //   khat[d*dim+e][p] = sum_q w d_d(phi_a) d_e(phi_b)
+  //   chat[n*dim+d][p] = sum_q w phi_a phi_n d_d(phi_b)
+  double khat[9][kMaxNN * kMaxNN];
+  double chat[kMaxNN * 3][kMaxNN * kMaxNN];
 };
 
 namespace fe_detail {
@@ -135,6 +140,21 @@ inline bool fill_fe_tables(int dim, int rule, FeTables &T) {
       double s = 0;
       for (int q = 0; q < T.nq; ++q) s += T.w[q] * T.phi[q][a] * T.phi[q][b];
       T.mhat[a][b] = s;
+    }
+    for (int b = 0; b < T.nn; ++b) {
+      const int p = a * T.nn + b;
+      for (int d = 0; d < dim; ++d)
+        for (int e = 0; e < dim; ++e) {
+          double s = 0;
+          for (int q = 0; q < T.nq; ++q) s += T.w[q] * T.dphi[q][a][d] * T.dphi[q][b][e];
+          T.khat[d * dim + e][p] = s;
+        }
+      for (int n = 0; n < T.nn; ++n)
+        for (int d = 0; d < dim; ++d) {
+          double s = 0;
+          for (int q = 0; q < T.nq; ++q) s += T.w[q] * T.phi[q][a] * T.phi[q][n] * T.dphi[q][b][d];
+          T.chat[n * dim + d][p] = s;
+        }
     }
     {
       double s = 0;  // the absolute value is taken per (q, j) term, as in the reference

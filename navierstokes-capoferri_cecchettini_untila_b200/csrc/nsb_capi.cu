@@ -708,7 +708,6 @@ void assemble_launch(nsb_ctx *c) {
   A.fs_val = c->fs.val.p;
   A.val01 = c->a01.val.p;
   A.val10 = c->a10.val.p;
-  A.val10t = c->a10t.p;
   A.n_own_nodes = c->n_own_nodes;
   A.p_begin = c->p_begin;
   A.n_p_own = c->n_p_own;
@@ -721,16 +720,17 @@ void assemble_launch(nsb_ctx *c) {
   c->fs.val.zero(c->stream);
   c->a01.val.zero(c->stream);
   c->a10.val.zero(c->stream);
-  c->a10t.zero(c->stream);
   c->rhs.zero(c->stream);
   const unsigned grid =
       (unsigned)std::min<int64_t>((c->n_cells + kAsmWarps - 1) / kAsmWarps, (int64_t)kNumSM * 8);
   if (c->dim == 2)
-    NSB_LAUNCH(c, (assemble_cells_kernel<2, 7>), grid, kAsmWarps * 32, A);
-  else if (c->fe_host.nq == 10)
-    NSB_LAUNCH(c, (assemble_cells_kernel<3, 10>), grid, kAsmWarps * 32, A);
+    NSB_LAUNCH(c, assemble_cells_kernel<2>, grid, kAsmWarps * 32, A);
   else
-    NSB_LAUNCH(c, (assemble_cells_kernel<3, 14>), grid, kAsmWarps * 32, A);
+    NSB_LAUNCH(c, assemble_cells_kernel<3>, grid, kAsmWarps * 32, A);
+  // A10 transposed on the pattern of A01 (feeds S = B Di Bt): before the Dirichlet rows are cleared the two
+  // blocks hold the same numbers, -int d_c(phi_a) psi_k (reference :222-229), so it is a copy, not a second scatter
+  NSB_CUDA(cudaMemcpyAsync(c->a10t.p, c->a01.val.p, (size_t)c->a01.nnz * sizeof(double), cudaMemcpyDeviceToDevice,
+                           c->stream));
   // reference :326-328
   if (c->bc_nodes.n) {
     const int64_t nb = (int64_t)c->bc_nodes.n;
