@@ -895,6 +895,14 @@ void auto_inner(nsb_ctx *c) {
   }
 }
 
+void schur_outer(nsb_ctx *c, const double *diag) {
+  const int64_t n_nodes = c->n_u / c->dim;
+  if (c->dim == 2)
+    NSB_LAUNCH(c, schur_outer_kernel<2>, blocks_for(n_nodes * 32), 256, c->a01.view(), c->a10t.p, diag, c->s.view());
+  else
+    NSB_LAUNCH(c, schur_outer_kernel<3>, blocks_for(n_nodes * 32), 256, c->a01.view(), c->a10t.p, diag, c->s.view());
+}
+
 // lumped velocity mass of the reference (:232-236), geometry only: computed at first use
 void ensure_lumped(nsb_ctx *c) {
   if (c->lumped.p) return;
@@ -924,8 +932,7 @@ void prec_init(nsb_ctx *c) {
     sdiag = c->dtm.p;
   }
   c->s.val.zero(c->stream);
-  NSB_LAUNCH(c, schur_outer_kernel, blocks_for((int64_t)c->n_u * 32), 256, c->a01.view(), c->a10t.p, sdiag,
-             c->s.view());
+  schur_outer(c, sdiag);
   allreduce_sum(c, c->s.val.p, (size_t)c->s.nnz);
   NSB_LAUNCH(c, diag_inverse_kernel, blocks_for(c->n_p), 256, (int64_t)c->n_p, 1, c->s.val.p, c->diagS.p, c->dis.p);
   const int its = c->eig_warm ? 6 : 30;
@@ -1633,8 +1640,7 @@ int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
         case 2: prec_apply(c, c->rhs.p, c->V.p); break;
         case 3:
           c->s.val.zero(c->stream);
-          NSB_LAUNCH(c, schur_outer_kernel, blocks_for((int64_t)c->n_u * 32), 256, c->a01.view(), c->a10t.p, c->di.p,
-                     c->s.view());
+          schur_outer(c, c->di.p);
           break;
         case 4: fs_cheb_sweep(c, c->chd_u.p, c->chzA.p, c->chzB.p, c->chz_u.p, 0.5, 0.5); break;
         case 6: cheb_sweep(c, c->s, c->dis.p, c->vec1.p, c->chz_p.p, c->chd_p.p, c->chz_p2.p, 0.5, 0.5); break;

@@ -128,23 +128,30 @@ __global__ void diag_inverse_kernel(int64_t n, int rep, const double *__restrict
 }
 
 // S = B diag(Di) Bt on the precomputed pattern of S (reference :956), as a sum
-// of outer products over the velocity rows this rank owns:
-//   S[V,W] += B[V,u] Di[u] Bt[u,W],  B[V,u] = a10t[u,V] (pattern of row u of A01).
-// One warp per velocity dof; lanes stride over the (V,W) pairs of the row.  On
-// several GPUs every rank adds its owned rows and the values are all-reduced.
+// of outer products over the velocity NODES this rank owns: the dim rows of a node
+// share their pattern in A01 and their Di, so
+//   S[V,W] += Di[a] sum_c B[V,(a,c)] Bt[(a,c),W],  B[V,u] = a10t[u,V] (pattern of row u of A01),
+// one atomic per (V,W) pair and node instead of per dof.  One warp per node; lanes
+// stride over the (V,W) pairs of the row.  On several GPUs every rank adds its
+// owned rows and the values are all-reduced.
+template <int DIM>
 __global__ void __launch_bounds__(256) schur_outer_kernel(CsrView Bt, const double *__restrict__ a10t,
                                                           const double *__restrict__ di, CsrView S) {
-  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (u >= Bt.n_rows) return;
-  const int64_t b = Bt.rowptr[u];
-  const int len = (int)(Bt.rowptr[u + 1] - b);
-  const double d = di[u];
+  if (DIM * a >= Bt.n_rows) return;
+  int64_t b[DIM];
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) b[c] = Bt.rowptr[DIM * a + c];
+  const int len = (int)(Bt.rowptr[DIM * a + 1] - b[0]);
+  const double d = di[DIM * a];
   for (int p = lane; p < len * len; p += 32) {
     const int i = p / len, j = p % len;
-    const double t = Bt.val[b + j];
+    double t = 0.0;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) t += a10t[b[c] + i] * Bt.val[b[c] + j];
     if (t == 0.0) continue;  // constrained rows of Bt are zero
-    const uint32_t V = Bt.colind[b + i], W = Bt.colind[b + j];
+    const uint32_t V = Bt.colind[b[0] + i], W = Bt.colind[b[0] + j];
     int64_t lo = S.rowptr[V], hi = S.rowptr[V + 1];
     while (lo < hi) {
       const int64_t mid = (lo + hi) >> 1;
@@ -153,7 +160,7 @@ __global__ void __launch_bounds__(256) schur_outer_kernel(CsrView Bt, const doub
       else
         hi = mid;
     }
-    atomicAdd(S.val + lo, a10t[b + i] * d * t);
+    atomicAdd(S.val + lo, d * t);
   }
 }
 
