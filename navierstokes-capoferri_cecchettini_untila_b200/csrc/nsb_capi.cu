@@ -338,14 +338,13 @@ void cheb_solve_F(nsb_ctx *c, const double *b, double *out, int k, double lmax, 
   else
     NSB_LAUNCH(c, fs_cheb_first_kernel<3>, blocks_for(n), 256, n, c->din.p, b, 1.0 / theta, bd, z);
   if (k <= 1) return;
-  NSB_CUDA(cudaMemsetAsync(zold, 0, (size_t)n * sizeof(double), c->stream));  // z_0 = 0
   double rho = 1.0 / sigma;
   for (int i = 1; i < k; ++i) {
     const double rho_new = 1.0 / (2.0 * sigma - rho);
     const bool last = i == k - 1;
     halo_exchange(c, z);
     double *target = last ? out : znew;
-    fs_cheb_sweep(c, bd, z, zold, target, rho_new * rho, 2.0 * rho_new / delta);
+    fs_cheb_sweep(c, bd, z, i == 1 ? nullptr : zold, target, rho_new * rho, 2.0 * rho_new / delta);  // z_0 = 0
     // rotate: zold <- z, z <- target, the old zold becomes the next target
     double *freed = zold;
     zold = z;

@@ -382,7 +382,8 @@ __global__ void __launch_bounds__(kSlabThreads, kSlabMinBlocks)
     const double sc = slab_row_sum<DIM>(sm, S.vpos[r], (int)(i % DIM));
     const int64_t g = (int64_t)DIM * r0 + i;
     const double zg = __ldg(z + g);
-    znew[g] = zg + c1 * (zg - zold[g]) + c2 * (bd[g] - dinv_node[r] * sc);
+    const double zo = zold != nullptr ? zold[g] : 0.0;  // nullptr: z_0 = 0 (second sweep of a solve)
+    znew[g] = zg + c1 * (zg - zo) + c2 * (bd[g] - dinv_node[r] * sc);
   }
 }
 
