@@ -18,10 +18,13 @@
 //     shared memory once, with coalesced loads, so every vector sector is
 //     fetched once per slab instead of once per non-zero;
 //   * the virtual rows sorted by length and stored as 8 ELL slices of 32 rows
-//     (column-major inside a slice): thread t of the CTA owns virtual row t and
-//     streams `val` (8 B) and a 16-bit window-local column index (2 B) with
-//     perfectly coalesced 256 B + 64 B warp loads -- 10 B per non-zero instead
-//     of 12 B, no row pointers, no shuffles;
+//     (entry-major inside a slice, two entries of a lane adjacent): thread t of
+//     the CTA owns virtual row t and streams `val` (8 B) and a 16-bit
+//     window-local column index (2 B) with coalesced 512 B + 128 B warp loads
+//     -- 10 B per non-zero instead of 12 B, no row pointers, no shuffles;
+//   * the order of the entries inside a virtual row is chosen so that the 16
+//     lanes of a half-warp read different shared-memory bank pairs (pass 3 of
+//     build_slabs);
 //   * per real row a packed word with the thread positions of its <= 3 chunks;
 //     partial sums are combined in a fixed order (deterministic) in the
 //     coalesced epilogue that also applies the vector update of the sweep.
@@ -54,8 +57,8 @@ struct SlabView {
 
 // Position of entry k of lane `lane` inside a slice: two consecutive entries of a lane are adjacent, so
 // a lane fetches 2 values with one 128-bit load and 2 indices with one 32-bit load (512 B + 128 B per
-// warp request instead of 256 B + 64 B: measured on B200, the matrix stream is limited by the number
-// of requests in flight, not by their bytes).  Slice widths are even.
+// warp request; on B200 this measured 1 % faster than 256 B + 64 B requests).  Slice widths are even, which
+// also gives the bank-aware schedule slack to avoid conflicts.
 __host__ __device__ inline int64_t slab_entry_pos(int k, int lane) { return (int64_t)(k >> 1) * 64 + lane * 2 + (k & 1); }
 
 struct SlabHost {
@@ -166,7 +169,8 @@ inline SlabHost build_slabs(int64_t n_rows, int64_t n_cols, const int64_t *rp, c
   // conflict wavefronts per shared load, L1/shared pipe the busiest unit of the sweep kernel at 73 %.
   uint32_t maxw = 0;
   int64_t wavefronts = 0, steps = 0, bound = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(max : maxw) reduction(+ : wavefronts, steps, bound)
+  int sched_error = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : maxw, sched_error) reduction(+ : wavefronts, steps, bound)
   for (int64_t s = 0; s < ns; ++s) {
     const uint32_t *wb = H.win_list.data() + H.win_ptr[s], *we = H.win_list.data() + H.win_ptr[s + 1];
     const uint32_t nw = (uint32_t)(we - wb);
@@ -266,9 +270,10 @@ inline SlabHost build_slabs(int64_t n_rows, int64_t n_cols, const int64_t *rp, c
         ++steps;
       }
       for (int l = 0; l < 16; ++l)
-        if (rem[l] != 0) throw StructError("slab storage: internal scheduling error");
+        if (rem[l] != 0) sched_error = 1;  // (exceptions must not leave an OpenMP region)
     }
   }
+  if (sched_error) throw StructError("slab storage: internal scheduling error");
   H.bank_wavefronts_per_step = steps ? (double)wavefronts / (double)steps : 1.0;
   H.bank_wavefronts_bound = steps ? (double)bound / (double)steps : 1.0;
   H.max_window = maxw;
@@ -465,15 +470,22 @@ inline GSlabHost build_gslabs(int dim, const std::vector<uint32_t> &slab_row, co
   std::vector<int64_t> slice_len((size_t)ns * kSlabSlices, 0);
   H.perm.assign((size_t)n_nodes, 0);
   uint32_t maxw = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(max : maxw)
+  int gerr = 0;  // (exceptions must not leave an OpenMP region)
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : maxw, gerr)
   for (int64_t s = 0; s < ns; ++s) {
     const int64_t a0 = slab_row[s], na = (int64_t)slab_row[s + 1] - a0;
-    if (na > kSlabThreads) throw StructError("slab storage: more nodes than threads in a slab");
+    if (na > kSlabThreads) {
+      gerr = 1;
+      continue;
+    }
     std::vector<uint32_t> &w = wins[s];
     for (int64_t a = a0; a < a0 + na; ++a) w.insert(w.end(), ci + rp[dim * a], ci + rp[dim * a + 1]);
     std::sort(w.begin(), w.end());
     w.erase(std::unique(w.begin(), w.end()), w.end());
-    if (w.size() > 65535) throw StructError("slab storage: pressure window exceeds 16-bit indices");
+    if (w.size() > 65535) {
+      gerr = 2;
+      continue;
+    }
     maxw = std::max(maxw, (uint32_t)w.size());
     std::vector<uint16_t> order((size_t)na);
     for (int64_t i = 0; i < na; ++i) order[i] = (uint16_t)i;
@@ -482,6 +494,8 @@ inline GSlabHost build_gslabs(int dim, const std::vector<uint32_t> &slab_row, co
     for (int64_t i = 0; i < na; ++i) H.perm[(size_t)(a0 + i)] = order[i];
     for (int64_t wv = 0; wv * 32 < na; ++wv) slice_len[s * kSlabSlices + wv] = 32 * len(a0 + order[wv * 32]);
   }
+  if (gerr == 1) throw StructError("slab storage: more nodes than threads in a slab");
+  if (gerr == 2) throw StructError("slab storage: pressure window exceeds 16-bit indices");
   H.max_window = maxw;
   H.pwin_ptr.assign((size_t)ns + 1, 0);
   for (int64_t s = 0; s < ns; ++s) H.pwin_ptr[s + 1] = H.pwin_ptr[s] + (uint32_t)wins[s].size();
@@ -490,7 +504,7 @@ inline GSlabHost build_gslabs(int dim, const std::vector<uint32_t> &slab_row, co
   for (size_t i = 0; i < slice_len.size(); ++i) H.slice_ptr[i + 1] = H.slice_ptr[i] + slice_len[i];
   H.idx.assign((size_t)H.slice_ptr.back(), 0);
   H.src.assign((size_t)H.slice_ptr.back() * dim, kSlabPad);
-#pragma omp parallel for schedule(dynamic, 64)
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : gerr)
   for (int64_t s = 0; s < ns; ++s) {
     const std::vector<uint32_t> &w = wins[s];
     std::copy(w.begin(), w.end(), H.pwin_list.begin() + H.pwin_ptr[s]);
@@ -503,12 +517,13 @@ inline GSlabHost build_gslabs(int dim, const std::vector<uint32_t> &slab_row, co
       for (int64_t k = 0; k < n; ++k) {
         H.idx[(size_t)(base + 32 * k + lane)] = (uint16_t)(std::lower_bound(w.begin(), w.end(), ci[r0 + k]) - w.begin());
         for (int c = 0; c < dim; ++c) {
-          if (ci[rp[dim * a + c] + k] != ci[r0 + k]) throw StructError("A01: the rows of a velocity node do not have the same pattern");
+          if (ci[rp[dim * a + c] + k] != ci[r0 + k]) gerr = 3;
           H.src[(size_t)gslab_val_pos(dim, base, (int)k, c, lane)] = (uint32_t)(rp[dim * a + c] + k);
         }
       }
     }
   }
+  if (gerr == 3) throw StructError("A01: the rows of a velocity node do not have the same pattern");
   return H;
 }
 
