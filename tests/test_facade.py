@@ -29,6 +29,20 @@ def test_reference_drivers_compile_unmodified_against_facade(pkg, tmp_path, case
     assert r.returncode == 0, r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("prec", ["NSB_PREC_AYOSIDA", "NSB_PREC_IDENTITY"])
+def test_facade_builds_with_the_alternative_preconditioners(pkg, tmp_path, prec):
+    """The reference selects PreconditionAYosida / PreconditionIdentity by (un)commenting blocks of
+    NavierStokes.cpp:352-373; the facade takes -DNS_PRECONDITIONER= instead."""
+    subprocess.check_call(["make", "-C", ROOT, "host", "cuda"], stdout=subprocess.DEVNULL)
+    out = str(tmp_path / "drv")
+    cmd = ["/usr/bin/g++", "-O0", "-std=c++17", "-fopenmp", "-DDIM=2", "-DNS_INPUT=", f"-DNS_PRECONDITIONER={prec}",
+           "-I" + os.path.join(PKG_DIR, "host"), "-I" + os.path.join(ROOT, "include"), "-o", out,
+           os.path.join(PKG_DIR, "drivers", "d2_test_01.cpp"), os.path.join(PKG_DIR, "host", "NavierStokes.cpp"),
+           "-L" + PKG_DIR, "-lnsb_host", "-lnsb", "-Wl,-rpath," + PKG_DIR]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
 def _run_driver(tmp_path, binary, mesh_name, h, T):
     subprocess.check_call(["make", "-C", ROOT, "drivers"], stdout=subprocess.DEVNULL)
     for d in ("build", "output", "cache", "mesh"):
