@@ -133,6 +133,10 @@ int nsb_vmult(nsb_ctx *ctx, const double *x_host, double *y_host);
  * storage the solver uses, 6 Chebyshev sweep on S, 7 dst0 = vec0 - Di .* (A01 p), 8 vec1 = src1 - A10 u.
  * Add 0x100 to flush L2 between repetitions. */
 int nsb_bench_kernel(nsb_ctx *ctx, int which, int reps, double *ms_mean);
+/* CUDA-event bracket on the context's stream: everything the calls in between enqueue, including the gaps the
+ * host-sequenced GMRES leaves, is inside the measured interval (bench.py times its K steps with it). */
+int nsb_timer_start(nsb_ctx *ctx);
+int nsb_timer_stop(nsb_ctx *ctx, double *elapsed_ms);
 /* Launch counter of this context's own kernels (for bench.py gpu_launches). */
 int64_t nsb_launch_count(const nsb_ctx *ctx);
 /* timers of the last step in ms: [0] assemble, [1] prec init, [2] solve, [3] forces */

@@ -30,7 +30,7 @@ using namespace nsb;
 struct nsb_ctx {
   int dim = 0, device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;  // ev_t*: nsb_timer_start/stop
   std::string err;
   int64_t dev_bytes = 0, launches = 0;
   // sizes
@@ -1181,6 +1181,8 @@ int nsb_create(int dim, int device_id, nsb_ctx **out) {
     NSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     NSB_CUDA(cudaEventCreate(&c->ev0));
     NSB_CUDA(cudaEventCreate(&c->ev1));
+    NSB_CUDA(cudaEventCreate(&c->ev_t0));
+    NSB_CUDA(cudaEventCreate(&c->ev_t1));
     c->errflag.alloc(1, &c->dev_bytes);
     c->errflag.zero(c->stream);
   });
@@ -1209,6 +1211,8 @@ void nsb_destroy(nsb_ctx *c) {
   }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   cudaStream_t s = c->stream;
   delete c;
   if (s) cudaStreamDestroy(s);
@@ -1654,6 +1658,22 @@ int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
       total += ms;
     }
     *ms_mean = total / reps;
+  });
+}
+
+int nsb_timer_start(nsb_ctx *c) {
+  return guarded(c, [&] {
+    NSB_CUDA(cudaStreamSynchronize(c->stream));
+    NSB_CUDA(cudaEventRecord(c->ev_t0, c->stream));
+  });
+}
+int nsb_timer_stop(nsb_ctx *c, double *ms) {
+  return guarded(c, [&] {
+    NSB_CUDA(cudaEventRecord(c->ev_t1, c->stream));
+    NSB_CUDA(cudaEventSynchronize(c->ev_t1));
+    float f = 0;
+    NSB_CUDA(cudaEventElapsedTime(&f, c->ev_t0, c->ev_t1));
+    if (ms) *ms = f;
   });
 }
 

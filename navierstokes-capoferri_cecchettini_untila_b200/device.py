@@ -23,6 +23,7 @@ SYMBOLS = [
     "nsb_bench_kernel", "nsb_launch_count", "nsb_timers", "nsb_info", "nsb_alloc_pinned", "nsb_free_pinned",
     "nsb_comm_unique_id", "nsb_comm_init", "nsb_set_local_dofs", "nsb_set_halo", "nsb_set_schur_solver", "nsb_gather_velocity",
     "nsb_slab_host_check", "nsb_gslab_host_check", "nsb_get_lumped_mass_inv",
+    "nsb_timer_start", "nsb_timer_stop",
 ]
 
 
@@ -70,6 +71,8 @@ def device_lib():
         L.nsb_get_lumped_mass_inv.argtypes = [p, f64p]
         L.nsb_vmult.argtypes = [p, f64p, f64p]
         L.nsb_bench_kernel.argtypes = [p, C.c_int, C.c_int, f64p]
+        L.nsb_timer_start.argtypes = [p]
+        L.nsb_timer_stop.argtypes = [p, f64p]
         L.nsb_launch_count.argtypes = [p]
         L.nsb_launch_count.restype = C.c_int64
         L.nsb_timers.argtypes = [p, f64p]
@@ -305,6 +308,15 @@ class Device:
         out = np.empty(self.N, np.float64)
         self._chk(self.L.nsb_get_rhs(self.h, _p(out, C.c_double)))
         return out
+
+    def timer_start(self):
+        self._chk(self.L.nsb_timer_start(self.h))
+
+    def timer_stop(self):
+        """Milliseconds between timer_start and now, measured with CUDA events on the context's stream."""
+        ms = C.c_double()
+        self._chk(self.L.nsb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def lumped_mass_inv(self, n_u):
         """deltat_lumped_mass_inv of the reference, velocity block (n_u values)."""
