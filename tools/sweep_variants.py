@@ -1,7 +1,17 @@
 #!/usr/bin/env python
-"""Experiment driver (not part of the product): times kernel variants of the slab sweep on one
+"""Experiment driver (not part of the product), kept as the record of how the slab sweep kernel was tuned in
+round 1: it timed kernel variants (load batch, resident CTAs, prefetch, cp.async window fill, window capacity,
+entry scheduling) selected through NSB_SLAB_VARIANT / NSB_SLAB_SCHED / NSB_SLAB_WINDOW on one resident problem,
+one process per configuration.  Those switches were compiled out once the configuration was frozen
+(csrc/slab.cuh: kSlabBatch, kSlabMinBlocks); results: profiles/r1_slab_kernels.md.  With the current library every
+configuration times the same (adopted) kernel.  usage: sweep_variants.py [h]"""Experiment driver (not part of the product): times kernel variants of the slab sweep on one
 resident problem.  Each configuration runs in its own process because the variant / layout
-switches are read once per process.  usage: sweep_variants.py [h]"""
+switches are read once per process.  usage: sweep_variants.py [h]"""Experiment driver (not part of the product), kept as the record of how the slab sweep kernel was tuned in
+round 1: it timed kernel variants (load batch, resident CTAs, prefetch, cp.async window fill, window capacity,
+entry scheduling) selected through NSB_SLAB_VARIANT / NSB_SLAB_SCHED / NSB_SLAB_WINDOW on one resident problem,
+one process per configuration.  Those switches were compiled out once the configuration was frozen
+(csrc/slab.cuh: kSlabBatch, kSlabMinBlocks); results: profiles/r1_slab_kernels.md.  With the current library every
+configuration times the same (adopted) kernel.  usage: sweep_variants.py [h]"""
 import importlib, json, os, subprocess, sys, time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
