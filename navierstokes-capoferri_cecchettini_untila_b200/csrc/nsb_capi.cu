@@ -92,7 +92,7 @@ struct nsb_ctx {
   bool have_mesh = false, have_dofs = false, have_quad = false, finalized = false;
   double t_ms[4] = {0, 0, 0, 0};
   DevBuf<char> flush;
-  int spmv_L = 16;
+  int spmv_L = 8;  // lanes per row of the canonical-CSR product (bench): 8 -> 2.52 ms, 16 -> 2.87, 32 -> 3.67, 4 -> 3.02
   // ---- domain decomposition (one process per GPU) ----
   // Velocity rows are distributed: local nodes [0,n_own) are owned, [n_own,n_own+n_ghost) are
   // ghosts refreshed by halo exchange.  Pressure vectors and S are replicated; this rank owns the
@@ -240,9 +240,11 @@ void allgather_p(nsb_ctx *c, double *yp) {
   NSB_NCCL(nccl().GroupEnd());
 }
 
+// lanes per CSR row.  Measured on B200 (9.7 M DoFs): S (53 entries per row) 8 lanes 0.078 ms, 16 lanes 0.092;
+// canonical A00 (81 per row) 8 lanes 2.52 ms, 16 lanes 2.87; A10 (169 per row) 32 lanes 0.186 ms, 16 lanes 0.234.
 int pick_L(const CsrDev &A) {
   const double mean = A.n_rows ? (double)A.nnz / (double)A.n_rows : 0.0;
-  return mean < 12 ? 4 : mean < 40 ? 8 : mean < 120 ? 16 : 32;
+  return mean < 12 ? 4 : mean < 100 ? 8 : mean < 140 ? 16 : 32;
 }
 
 // y = A x (mode 0), w - A x (1), w - d.*(A x) (2), d.*(A x) (3)

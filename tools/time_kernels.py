@@ -10,9 +10,17 @@ dev = pkg.Device(3, 0).load_problem(prob, node_pattern=True)
 dev.set_params(0.01, prob.mean_velocity(0.0) * 0.4 / 20)
 dev.set_solver(1e-6, 28, 10000, 0.5)
 dev.assemble(0.01)
-it, _, _ = dev.solve_time_step()
+if os.environ.get("NSB_TIME_ONLY"):
+    names = os.environ["NSB_TIME_ONLY"].split(",")
+    it = -1
+else:
+    names = None
+    it, _, _ = dev.solve_time_step()
 out = {"its": it}
-for name, which in (("sweep_F", 4), ("block_spmv", 5), ("prec_apply", 2), ("g_apply", 7), ("a10_spmv", 8), ("sweep_S", 6)):
+for name, which in (("sweep_F", 4), ("block_spmv", 5), ("prec_apply", 2), ("g_apply", 7), ("a10_spmv", 8), ("sweep_S", 6),
+                    ("canonical_spmv", 0)):
+    if names is not None and name not in names:
+        continue
     try:
         out[name + "_ms"] = round(dev.bench_kernel(which, 30), 4)
     except Exception as e:
