@@ -1,0 +1,44 @@
+"""External anchor for the oracle: the published Schaefer-Turek / DFG "2D-1" benchmark value.
+
+The reference's tests hold no golden vectors, and its own Cd/Cl use a non-standard
+force formula and D = 0.4 (quirks B1-B4), so literature drag/lift do not apply to them.  The pressure
+difference between the front and the back of the cylinder, dP = p(0.15, 0.2) - p(0.25, 0.2), is read
+straight off the solution vector and is free of those quirks: with nu = 1e-3 (true Re = 20) the
+steady value is 0.11752016697 (Schaefer & Turek 1996; featflow.de DFG benchmark 2D-1).  The oracle --
+naive assembly, boundary rows, semi-implicit time stepping, GMRES + aSIMPLE -- reproduces it to 0.3 %
+on a 12 k-DoF mesh."""
+import numpy as np
+
+DP_LITERATURE = 0.11752016697
+
+
+def test_oracle_reproduces_dfg_2d1_pressure_drop(pkg, oracle_mod):
+    prob = pkg.Problem.generate("2d-cylinder", 0.03).build(inlet=(pkg.INLET_PARABOLIC, 0.3, 0.41, 0))
+    xyz = prob.array("xyz").reshape(-1, 2)
+    cells = prob.array("cells").astype(np.int64)
+    pdof = np.full(xyz.shape[0], -1, np.int64)
+    pdof[cells] = prob.array("cell_pverts").astype(np.int64)  # pressure dof (block-local) of every mesh vertex
+    orc = oracle_mod.Oracle(2, prob.array("xyz"), prob.array("cells"), prob.array("bfaces"), prob.array("bids"))
+    orc.set_inlet(0, 0.3, 0.41, 0)       # U_max = 0.3 -> U_mean = 0.2 (tests/2D/test_01)
+    dt = 0.02
+    orc.set_params(dt, 1e-3)             # nu = U_mean * 0.1 / 20, NOT set_re_number (which uses D = 0.4, quirk B1)
+    orc.set_threads(8)
+
+    def vertex_near(p):
+        d = np.linalg.norm(xyz - np.asarray(p), axis=1)
+        i = int(np.argmin(d))
+        assert d[i] < 2e-3  # the generator puts vertices at the stagnation points of the (polygonal) circle
+        return i
+
+    front, back = vertex_near((0.15, 0.2)), vertex_near((0.25, 0.2))
+    t, history = 0.0, []
+    for _ in range(100):                 # T = 2: the start-up transient has decayed (dP changes by < 1e-4 per unit time)
+        t += dt
+        orc.assemble(t)
+        rc, _, _, _ = orc.solve_time_step()
+        assert rc == 0
+        x = orc.solution()
+        history.append(x[orc.n_u + pdof[front]] - x[orc.n_u + pdof[back]])
+    dp = history[-1]
+    assert abs(history[-1] - history[-25]) < 2e-4, "not steady"
+    assert abs(dp - DP_LITERATURE) < 5e-3 * DP_LITERATURE, dp
