@@ -1,5 +1,5 @@
 import sys, importlib, numpy as np
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import conftest
 pkg = importlib.import_module("navierstokes-capoferri_cecchettini_untila_b200")
 from oracle import ns_oracle

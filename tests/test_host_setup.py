@@ -201,3 +201,8 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(base, f), errors="ignore").read()
                 assert "ns_oracle" not in txt and "oracle/" not in txt, os.path.join(base, f)
+    # the experiment scripts under tools/ are not checkers either
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".cu")):
+            txt = open(os.path.join(ROOT, "tools", f), errors="ignore").read()
+            assert "ns_oracle" not in txt and "from oracle" not in txt, f
