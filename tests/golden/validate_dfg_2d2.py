@@ -47,5 +47,10 @@ St = freq * 0.1 / 1.0
 out = {"h": h, "dt": dt, "T": T, "n_dofs": int(orc.N), "strouhal": float(St), "periods_used": int(len(cross) - 1),
        "lift_amplitude_reference_formula": float(0.5 * (tail.max() - tail.min())), "literature": [0.295, 0.305]}
 print(json.dumps(out))
-with open(os.path.join(ROOT, "tests", "golden", "dfg_2d2.json"), "w") as f:
-    json.dump(out, f, indent=1)
+# append the run to the committed record
+path = os.path.join(ROOT, "tests", "golden", "dfg_2d2.json")
+rec = json.load(open(path)) if os.path.exists(path) else {"runs": []}
+out.pop("literature", None)
+rec.setdefault("runs", []).append(out)
+with open(path, "w") as f:
+    json.dump(rec, f, indent=1)
