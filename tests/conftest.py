@@ -56,6 +56,23 @@ def make_case(pkg, oracle_mod, key, quad_rule=1, h=None):
     return prob, orc, dim, nu, um
 
 
+def make_configured_case(pkg, oracle_mod, mesh, h, uniform, um, re, dt, sin, nu=1e-3, quad_rule=1):
+    """Host problem + oracle with the parameters of one reference driver:
+    inlet profile, U_m, optional set_re_number(re) (evaluated at t = 0 like the drivers do), deltat and
+    the sin(pi t/8) inlet factor of the *_03 drivers.  Returns (prob, orc, dim, nu)."""
+    kind = pkg.INLET_UNIFORM if uniform else pkg.INLET_PARABOLIC
+    prob = pkg.Problem.generate(mesh, h).build(inlet=(kind, um, 0.41, 1 if sin else 0))
+    dim = prob.sizes()["dim"]
+    orc = oracle_mod.Oracle(dim, prob.array("xyz"), prob.array("cells"), prob.array("bfaces"), prob.array("bids"),
+                            quad_rule)
+    orc.set_inlet(kind, um, 0.41, 1 if sin else 0)
+    orc.set_params(dt, nu)
+    if re is not None:
+        nu = orc.set_re_number(re)
+    orc.set_threads(min(8, os.cpu_count() or 1))
+    return prob, orc, dim, nu
+
+
 def seeded_state(orc, seed=1234):
     """A smooth-ish seeded velocity/pressure state so that the convective term is
     non-zero."""
