@@ -24,8 +24,8 @@ cuda: $(PKG)/libnsb.so
 $(PKG)/libnsb_host.so: $(HOST_SRC) $(HOST_HDR)
 	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRC)
 
-oracle/libns_oracle.so: oracle/ns_oracle.cpp oracle/ns_oracle.h
-	$(CXX) $(CXXFLAGS) -shared -o $@ oracle/ns_oracle.cpp
+oracle/libns_oracle.so: oracle/ns_oracle.cpp oracle/ns_baseline.cpp oracle/ns_oracle.h oracle/ns_oracle_internal.h
+	$(CXX) $(CXXFLAGS) -shared -o $@ oracle/ns_oracle.cpp oracle/ns_baseline.cpp
 
 $(PKG)/libnsb.so: $(CU_SRC) $(CU_HDR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRC) -cudart static -ldl 2> $(PKG)/csrc/ptxas.log || (cat $(PKG)/csrc/ptxas.log; false)

@@ -4,7 +4,13 @@
 the dominant kernel.
 
     python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a path)
-    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference, all host cores
+
+The CPU arm cannot run the 9.67 M-DoF headline workload in minutes (about 10 minutes per step and >20 GB for
+the canonical block matrix and its ILU factors), so it runs BASELINE.json's config C3 (3d-square, h = 0.05,
+tests/3D/test_01 parameters) for the W + K steps it is asked for and prints THAT config, the steps it really
+timed and the measured time; nothing is extrapolated into `value`.  The native arm times the same C3 mesh as
+well (`c3` in its line), so one measured same-config pair exists.
 
 One "step" = NavierStokes::assemble + solve_time_step + compute_forces
 (reference src/NavierStokes.cpp:483-486) on the `3d-cylinder` mesh
@@ -14,6 +20,7 @@ line on rank 0.
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import importlib
 import json
 import os
@@ -41,7 +48,10 @@ def parse():
     ap.add_argument("--mesh", default="3d-cylinder")
     ap.add_argument("--h", type=float, default=float(os.environ.get("NSB_BENCH_H", "0.011")),
                     help="target edge length of the mesh (0.011 ~ 10M DoFs)")
-    ap.add_argument("--cpu-h", type=float, default=0.05, help="mesh of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-mesh", default="3d-square", help="mesh of the CPU arm / the paired C3 record")
+    ap.add_argument("--cpu-h", type=float, default=0.05, help="edge length of that mesh (0.05 = BASELINE config C3)")
+    ap.add_argument("--cpu-budget-s", type=float, default=300.0, help="wall-clock cap of the CPU arm's timed loop")
+    ap.add_argument("--no-c3", action="store_true", help="skip the paired C3 record of the native arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-canonical-spmv", action="store_true",
                     help="skip y = A x on the materialised canonical (reference) block CSR (12 B x 9 nnz(F_s) + ... "
@@ -159,9 +169,13 @@ def assembly_bytes(info, dim=3):
 
 
 # --------------------------------------------------------------------------
-def cpu_reference_run(pkg, mesh, h, steps, warmup, threads):
-    """The CPU restatement of the reference algorithm (oracle) on a bounded
-    sample mesh of the same geometry; returns (ms/step, n_dofs, iters)."""
+def cpu_arm(pkg, mesh, h, steps, warmup, threads, budget_s=1e9, serial=False):
+    """The CPU restatement of the reference algorithm (oracle/: naive (q,i,j) assembly, GMRES(28) + aSIMPLE with
+    ILU(0)-preconditioned inner GMRES to 1e-2) on `mesh` at edge length `h`, tests/3D/test_01 parameters.
+    serial=False: the way `mpirun -n threads` runs it (oracle/ns_baseline.cpp: one subdomain per thread,
+    rank-local ILU(0), threaded SpMV / dots); serial=True: the single-thread checker itself.
+    Times `steps` steps after `warmup` (stops early when the timed loop exceeds budget_s) and returns the
+    measured figures of what really ran."""
     from oracle.ns_oracle import Oracle
     prob = pkg.Problem.generate(mesh, h).build(inlet=(pkg.INLET_PARABOLIC, U_M, H_CH, 0))
     dim = prob.sizes()["dim"]
@@ -169,18 +183,187 @@ def cpu_reference_run(pkg, mesh, h, steps, warmup, threads):
     orc.set_inlet(0, U_M, H_CH, 0)
     orc.set_params(DT, 1e-3)
     orc.set_re_number(RE)
-    orc.set_threads(threads)
-    t, times, iters = 0.0, [], []
+    if serial:
+        orc.set_threads(1)
+        asm, solve = orc.assemble, orc.solve_time_step
+    else:
+        part = np.array(prob.partition(threads)) if threads > 1 else np.zeros(orc.n_cells, np.int32)
+        orc.baseline_partition(threads, part)
+        asm, solve = orc.baseline_assemble, orc.baseline_solve_time_step
+    t, times, iters, phases, f = 0.0, [], [], [], None
+    t_loop = None
     for s in range(warmup + steps):
+        if s == warmup:
+            t_loop = time.perf_counter()
         t += DT
         t0 = time.perf_counter()
-        orc.assemble(t)
-        rc, it, _, _ = orc.solve_time_step()
-        orc.compute_forces(t)
+        asm(t)
+        t1 = time.perf_counter()
+        rc, it, tp, ts = solve()
+        f = orc.compute_forces(t)
+        t2 = time.perf_counter()
+        if rc != 0:
+            raise RuntimeError("CPU arm: GMRES did not converge")
         if s >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(t2 - t0)
             iters.append(it)
-    return 1e3 * float(np.mean(times)), orc.N, float(np.mean(iters))
+            phases.append((t1 - t0, tp, ts))
+            if time.perf_counter() - t_loop > budget_s:
+                break
+    ph = np.mean(np.array(phases), axis=0)
+    return {"ms_per_step": 1e3 * float(np.mean(times)), "steps_timed": len(times), "warmup_run": warmup,
+            "n_dofs": int(orc.N), "n_cells": int(orc.n_cells), "gmres_iters_per_step": float(np.mean(iters)),
+            "phase_ms": {"assemble": 1e3 * float(ph[0]), "prec_init": 1e3 * float(ph[1]), "solve": 1e3 * float(ph[2])},
+            "cd": float(f[2]), "cl": float(f[3]), "threads": 1 if serial else threads}
+
+
+CPU_ARM_TEXT = ("CPU restatement of the reference algorithm (oracle/: naive (q,i,j) assembly loop, GMRES(28) + aSIMPLE, "
+                "per-step SpGEMM for S, ILU(0)-preconditioned inner GMRES to 1e-2)")
+
+
+def cpu_config(a):
+    return {"workload": f"C3: {a.cpu_mesh} Re=20 (mesh/domain3D.geo geometry, tests/3D/test_01 parameters), h={a.cpu_h} "
+                        f"-- the largest BASELINE.json config the CPU arm completes in minutes; the native arm's "
+                        f"headline ({a.mesh} h={a.h}) is not CPU-runnable in this budget",
+            "mesh": a.cpu_mesh, "h": a.cpu_h, "deltat": DT, "Re": RE, "quadrature": "dealii95 (14-pt)",
+            "gmres": "left-preconditioned GMRES(28), rtol 1e-6 (reference stopping rule)",
+            "preconditioner": "aSIMPLE alpha=0.5, ILU(0)-preconditioned inner GMRES to 1e-2 (reference :934-995)",
+            "l2_policy": "n/a (CPU)", "parallelism": "one subdomain per host core, rank-local ILU(0)"}
+
+
+class NativeRun:
+    """One resident problem on this rank's GPU, stepped through the C ABI (include/nsb.h)."""
+
+    def __init__(self, pkg, a, mesh, h, dist, rank, world, local_rank):
+        self.pkg, self.a, self.dist, self.rank, self.world = pkg, a, dist, rank, world
+        t_setup = time.perf_counter()
+        prob = pkg.Problem.generate(mesh, h)
+        prob.build(inlet=(pkg.INLET_PARABOLIC, U_M, H_CH, 0), expand_a00=False)
+        sz = prob.sizes()
+        dim = sz["dim"]
+        loc = None
+        if world > 1:
+            prob.partition(world)  # same deterministic RCB partition on every rank
+            loc = pkg.LocalProblem(prob, world, rank)
+            ids = [pkg.Device.make_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            dev = pkg.Device(dim, local_rank).load_local_problem(prob, loc, ids[0])
+        else:
+            dev = pkg.Device(dim, local_rank).load_problem(prob, node_pattern=True)
+        nu = prob.mean_velocity(0.0) * 0.4 / RE  # set_re_number, reference :332-341
+        dev.set_params(DT, nu)
+        dev.set_solver(1e-6, 28, 10000, a.alpha)
+        kF, rF, kS, rS = a.sweeps.split(",")
+        dev.set_inner(int(kF), float(rF) if int(kF) > 0 else 0.0, int(kS), float(rS) if int(kS) > 0 else 0.0)
+        sm = a.schur.split(",")
+        dev.set_schur_solver(int(sm[0]), int(sm[1]), float(sm[2]), float(sm[3]), int(sm[4]))
+        self.prob, self.loc, self.dev, self.dim, self.sz = prob, loc, dev, dim, sz
+        self.N = sz["n_u"] + sz["n_p"]   # global unknowns
+        self.N_loc = dev.N               # this rank's vector (owned + ghost velocity, replicated pressure)
+        self.info = dev.info()
+        self.t_setup = time.perf_counter() - t_setup
+        L = dev.L
+        if loc is None:
+            self.bc_dofs = np.array(prob.array("bc.dofs"))
+            bc_vals = prob.array("bc.values")
+        else:
+            bn = loc.array("bc_nodes")
+            self.bc_dofs = (dim * bn[:, None] + np.arange(dim, dtype=np.uint32)[None, :]).astype(np.uint32).ravel()
+            bc_vals = loc.array("bc_values")
+        self.pin_bc = L.nsb_alloc_pinned(8 * max(self.bc_dofs.size, 1))
+        self.pin_sol = L.nsb_alloc_pinned(8 * self.N_loc)
+        self.bc_host = np.frombuffer((C.c_char * (8 * self.bc_dofs.size)).from_address(self.pin_bc), dtype=np.float64)
+        self.sol_host = np.frombuffer((C.c_char * (8 * self.N_loc)).from_address(self.pin_sol), dtype=np.float64)
+        self.bc_host[:] = bc_vals
+        self.t = 0.0
+        self.iters, self.tasm, self.tprec, self.tsol = [], [], [], []
+        self.forces = None
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max_over_ranks(self, v):
+        if self.dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        if self.dist is None:
+            return np.asarray(v, np.float64)
+        import torch
+        t = torch.tensor(np.asarray(v, np.float64))
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.numpy()
+
+    def step(self, e2e):
+        dev = self.dev
+        self.t += DT
+        if e2e:  # the facade's per-step host traffic: Dirichlet values in, solution + forces out
+            dev.set_dirichlet(self.bc_dofs, self.bc_host)
+        dev.assemble(self.t)
+        it, tp, ts = dev.solve_time_step()
+        self.forces = dev.compute_forces(self.prob.mean_velocity(self.t))
+        if e2e:
+            dev.solution(out=self.sol_host)
+        tm = dev.timers()
+        self.iters.append(it)
+        self.tasm.append(tm[0])
+        self.tprec.append(tm[1])
+        self.tsol.append(tm[2])
+
+    def timed(self, steps, e2e):
+        """K steps between two CUDA events on the context's stream; max over ranks.  Returns
+        (ms/step by events, wall ms/step, launches, stats)."""
+        dev = self.dev
+        del self.iters[:], self.tasm[:], self.tprec[:], self.tsol[:]
+        l0 = dev.launch_count()
+        self.barrier()
+        t0 = time.perf_counter()
+        dev.timer_start()
+        for _ in range(steps):
+            self.step(e2e)  # every API call ends with a stream synchronise
+        ms_events = dev.timer_stop() / steps
+        self.barrier()
+        ms_wall = self.max_over_ranks(1e3 * (time.perf_counter() - t0) / steps)
+        stats = dict(iters=float(np.mean(self.iters)), asm=float(np.mean(self.tasm)), prec=float(np.mean(self.tprec)),
+                     sol=float(np.mean(self.tsol)))
+        return self.max_over_ranks(ms_events), ms_wall, dev.launch_count() - l0, stats
+
+    def measure(self, steps, warmup):
+        """warm-up, then `value` and `e2e` over THE SAME time steps: the state after the warm-up is saved and
+        restored between the two timed loops."""
+        for _ in range(warmup):
+            self.step(False)
+        snap, t_snap = self.dev.solution().copy(), self.t
+        ms_dev, ms_wall, launches, stats = self.timed(steps, False)
+        forces = self.forces.copy()
+        checks = self.checksums()
+        self.dev.set_solution(snap)
+        self.t = t_snap
+        ms_e2e, _, _, stats_e2e = self.timed(steps, True)
+        return dict(ms=ms_dev, wall=ms_wall, launches=launches, stats=stats, e2e=ms_e2e, forces=forces,
+                    e2e_iters=stats_e2e["iters"], checks=checks,
+                    h2d=int(8 * self.bc_dofs.size + 4 * self.bc_dofs.size), d2h=int(8 * self.N_loc + 32))
+
+    def checksums(self):
+        """Rank-count-invariant digests of the state after the timed steps: l2 norms of the velocity (owned
+        dofs summed over ranks) and of the (replicated) pressure."""
+        x = self.dev.solution()
+        n_u = self.dev.n_u
+        n_uloc = getattr(self.dev, "n_uloc", n_u)
+        u2 = float(self.sum_over_ranks([float(np.dot(x[:n_u], x[:n_u]))])[0])
+        p = x[n_uloc:]
+        return {"velocity_l2": u2 ** 0.5, "pressure_l2": float(np.dot(p, p)) ** 0.5}
+
+    def close(self):
+        L = self.dev.L
+        L.nsb_free_pinned(self.pin_bc)
+        L.nsb_free_pinned(self.pin_sol)
+        self.dev.close()
 
 
 def main():
@@ -201,125 +384,37 @@ def main():
         if rank != 0:
             return 0
         threads = os.cpu_count() or 1
-        ms, n_s, it = cpu_reference_run(pkg, a.mesh, a.cpu_h, max(1, min(a.steps, 2)), min(a.warmup, 1), threads)
-        prob = pkg.Problem.generate(a.mesh, a.h)
-        prob.build(inlet=(0, U_M, H_CH, 0), expand_a00=False)
-        n_full = prob.sizes()["n_u"] + prob.sizes()["n_p"]
-        val = ms * n_full / n_s
-        sample = (f"oracle (CPU restatement of the reference algorithm: naive (q,i,j) assembly, GMRES(28)+aSIMPLE+"
-                  f"ILU(0)+inner GMRES) on {a.mesh} h={a.cpu_h} ({n_s} DoFs, {it:.0f} GMRES its/step, "
-                  f"{ms:.0f} ms/step measured), scaled linearly in DoFs to the {n_full}-DoF workload; "
-                  f"assembly uses {threads} threads, the solve is serial like one Trilinos rank")
-        line = {"impl": "reference", "metric": "time_per_step", "value": val, "unit": "ms/step", "n_gpus": a.gpus,
-                "steps": a.steps, "warmup": a.warmup, "ms_per_step": val, "higher_is_better": False,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": "ms/step", "cores": threads, "kind": "port", "sample": sample},
-                "e2e": {"value": val, "unit": "ms/step", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        r = cpu_arm(pkg, a.cpu_mesh, a.cpu_h, a.steps, a.warmup, threads, budget_s=a.cpu_budget_s)
+        sample = (f"{CPU_ARM_TEXT} as `mpirun -n {threads}` runs it (one subdomain per core, rank-local ILU(0), "
+                  f"threaded SpMV/dots) on {a.cpu_mesh} h={a.cpu_h}: {r['n_dofs']} DoFs, {r['n_cells']} cells, "
+                  f"{r['steps_timed']} steps timed after {r['warmup_run']} warm-up steps, "
+                  f"{r['gmres_iters_per_step']:.1f} GMRES its/step; measured, nothing extrapolated")
+        line = {"impl": "reference", "metric": "time_per_step", "value": r["ms_per_step"], "unit": "ms/step",
+                "n_gpus": a.gpus, "steps": r["steps_timed"], "warmup": r["warmup_run"], "steps_requested": a.steps,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": cpu_config(a), "n_dofs": r["n_dofs"],
+                "n_cells": r["n_cells"], "gmres_iters_per_step": r["gmres_iters_per_step"], "phase_ms": r["phase_ms"],
+                "cd": r["cd"], "cl": r["cl"],
+                "cpu_baseline": {"value": r["ms_per_step"], "unit": "ms/step", "cores": threads, "kind": "port",
+                                 "sample": sample},
+                "e2e": {"value": r["ms_per_step"], "unit": "ms/step", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "paired_with": "the native arm's `c3` record (same mesh, same parameters, same number of steps)",
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return 0
 
     # ---------------- native arm ----------------
     dist = None
     if world > 1:  # one process per GPU (torchrun); gloo carries the NCCL id, barriers and the max over ranks
-        import torch
         import torch.distributed as dist
         dist.init_process_group("gloo")
-    t_setup = time.perf_counter()
-    prob = pkg.Problem.generate(a.mesh, a.h)
-    prob.build(inlet=(pkg.INLET_PARABOLIC, U_M, H_CH, 0), expand_a00=False)
-    sz = prob.sizes()
-    dim = sz["dim"]
-    loc = None
-    if world > 1:
-        prob.partition(world)  # same deterministic RCB partition on every rank
-        loc = pkg.LocalProblem(prob, world, rank)
-        ids = [pkg.Device.make_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        dev = pkg.Device(dim, local_rank).load_local_problem(prob, loc, ids[0])
-    else:
-        dev = pkg.Device(dim, local_rank).load_problem(prob, node_pattern=True)
-    nu = prob.mean_velocity(0.0) * 0.4 / RE  # set_re_number, reference :332-341
-    dev.set_params(DT, nu)
-    dev.set_solver(1e-6, 28, 10000, a.alpha)
-    dev.set_inner(int(kF), float(rF) if int(kF) > 0 else 0.0, int(kS), float(rS) if int(kS) > 0 else 0.0)
-    sm = a.schur.split(",")
-    dev.set_schur_solver(int(sm[0]), int(sm[1]), float(sm[2]), float(sm[3]), int(sm[4]))
-    info = dev.info()
-    N = sz["n_u"] + sz["n_p"]      # global unknowns
-    N_loc = dev.N                  # this rank's vector (owned + ghost velocity, replicated pressure)
-    t_setup = time.perf_counter() - t_setup
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    import ctypes as C
-    L = dev.L
-    if loc is None:
-        bc_dofs = np.array(prob.array("bc.dofs"))
-        bc_vals = prob.array("bc.values")
-    else:
-        bn = loc.array("bc_nodes")
-        bc_dofs = (dim * bn[:, None] + np.arange(dim, dtype=np.uint32)[None, :]).astype(np.uint32).ravel()
-        bc_vals = loc.array("bc_values")
-    pin_bc = L.nsb_alloc_pinned(8 * max(bc_dofs.size, 1))
-    pin_sol = L.nsb_alloc_pinned(8 * N_loc)
-    bc_host = np.frombuffer((C.c_char * (8 * bc_dofs.size)).from_address(pin_bc), dtype=np.float64)
-    sol_host = np.frombuffer((C.c_char * (8 * N_loc)).from_address(pin_sol), dtype=np.float64)
-    bc_host[:] = bc_vals
-
-    state = {"t": 0.0}
-    iters, tasm, tprec, tsol = [], [], [], []
-
-    def step(e2e):
-        state["t"] += DT
-        if e2e:  # the facade's per-step host traffic: Dirichlet values in, solution + forces out
-            dev.set_dirichlet(bc_dofs, bc_host)
-        dev.assemble(state["t"])
-        it, tp, ts = dev.solve_time_step()
-        f = dev.compute_forces(prob.mean_velocity(state["t"]))
-        if e2e:
-            dev.solution(out=sol_host)
-        tm = dev.timers()
-        iters.append(it)
-        tasm.append(tm[0])
-        tprec.append(tm[1])
-        tsol.append(tm[2])
-        return f
-
-    for _ in range(a.warmup):
-        step(False)
-    del iters[:], tasm[:], tprec[:], tsol[:]
+    run = NativeRun(pkg, a, a.mesh, a.h, dist, rank, world, local_rank)
+    dev, info, dim, N, N_loc = run.dev, run.info, run.dim, run.N, run.N_loc
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = dev.launch_count()
-    barrier()
-    t0 = time.perf_counter()
-    dev.timer_start()          # CUDA events on the stream all the kernels of this context run on
-    for _ in range(a.steps):
-        forces = step(False)   # every API call ends with a stream synchronise
-    ms_events = dev.timer_stop() / a.steps
-    barrier()
-    ms_wall = max_over_ranks(1e3 * (time.perf_counter() - t0) / a.steps)
-    ms_dev = max_over_ranks(ms_events)
-    launches = dev.launch_count() - l0
-    dev_stats = dict(iters=float(np.mean(iters)), asm=float(np.mean(tasm)), prec=float(np.mean(tprec)),
-                     sol=float(np.mean(tsol)))
-    # end to end through the C ABI with host buffers
-    barrier()
-    dev.timer_start()
-    for _ in range(a.steps):
-        forces = step(True)
-    ms_e2e = max_over_ranks(dev.timer_stop() / a.steps)
-    barrier()
+    m = run.measure(a.steps, a.warmup)
+    ms_dev, ms_wall, ms_e2e, launches, dev_stats, forces = m["ms"], m["wall"], m["e2e"], m["launches"], m["stats"], m["forces"]
+    run.barrier()
     # kernel micro-benchmarks on the resident system (CUDA events on the ctx stream)
     reps = 20
     ms_spmv = dev.bench_kernel(5, reps)
@@ -336,7 +431,7 @@ def main():
     sweep_gbs = sweep_bytes(info, dim) * gb / (ms_sweep * 1e-3)
     sweep_s_gbs = sweep_s_bytes(info) * gb / (ms_sweep_s * 1e-3)
     asm_gbs = assembly_bytes(info, dim) * gb / (ms_asm * 1e-3)
-    # share of one outer GMRES iteration: (kF-1) F sweeps, the fine-level S sweeps, one block product
+    # share of one outer GMRES iteration: the fine-level F passes, the fine-level S sweeps, one block product
     info2 = dev.info()
     kF_eff, kS_eff = info2["sweeps_F"], info2["sweeps_S"] + (1 if info2["schur_mode"] == 1 else 0)
     shares = {"fs_slab_sweep_kernel (Jacobi-type sweep on F, slab storage)": ((kF_eff - 1) * ms_sweep, sweep_gbs,
@@ -348,7 +443,7 @@ def main():
     top = max(shares, key=lambda k: shares[k][0])
     traffic = None
     try:  # measured DRAM bytes per launch of that kernel at this mesh size, when a capture exists (profiles/)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = tj.get(top.split(" ")[0], {}).get(str(a.h)) if world == 1 else None
     except Exception:
         pass
@@ -369,34 +464,60 @@ def main():
             "spmv_canonical_ms": ms_spmv_can,
             "spmv_canonical_frac_of_hbm": (spmv_canonical_bytes(info) * gb / (ms_spmv_can * 1e-3) / hbm_peak) if ms_spmv_can else None,
             "prec_apply_ms": ms_prec, "cd": float(forces[2]), "cl": float(forces[3]),
-            "setup_s": t_setup, "device_bytes": info["device_bytes"],
+            "rank_count_invariants": dict(m["checks"], cd=float(forces[2]), cl=float(forces[3]),
+                                          note="state after the timed steps; equal across --gpus N up to the GMRES tolerance"),
+            "setup_s": run.t_setup, "device_bytes": info["device_bytes"],
             "roofline": roof, "clocks": clocks,
-            "e2e": {"value": ms_e2e, "unit": "ms/step", "h2d_bytes_per_step": int(8 * bc_dofs.size + 4 * bc_dofs.size),
-                    "d2h_bytes_per_step": int(8 * N_loc + 32)},
+            "e2e": {"value": ms_e2e, "unit": "ms/step", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                    "same_steps_as_value": True, "gmres_iters_per_step": m["e2e_iters"]},
             "gpu_launches": int(launches)}
     if world > 1:
         line["n_dofs_local"] = N_loc
-        line["partition"] = "recursive coordinate bisection of the cells; velocity rows distributed, pressure replicated"
+        line["partition"] = "recursive coordinate bisection of the cells; velocity rows distributed"
+    run.barrier()
+    run.close()
     if rank != 0:
-        L.nsb_free_pinned(pin_bc)
-        L.nsb_free_pinned(pin_sol)
-        barrier()
-        dev.close()
         dist.destroy_process_group()
         return 0
+    if world == 1 and not a.no_c3:
+        # BASELINE.json config C3 on the same GPU: the mesh the CPU arm runs (paired same-config record)
+        c3 = NativeRun(pkg, a, a.cpu_mesh, a.cpu_h, None, 0, 1, local_rank)
+        mc = c3.measure(a.steps, a.warmup)
+        i3 = c3.info
+        mat_mb = (10 * (i3["nnz_a00"] // (dim * dim)) + 10 * i3["nnz_a01"] + 12 * i3["nnz_a10"] + 12 * i3["nnz_s"]) / 1e6
+        line["c3"] = {"workload": cpu_config(a)["workload"], "mesh": a.cpu_mesh, "h": a.cpu_h, "n_dofs": c3.N,
+                      "n_cells": i3["n_cells"], "steps": a.steps, "warmup": a.warmup, "ms_per_step": mc["ms"],
+                      "wall_ms_per_step": mc["wall"], "gmres_iters_per_step": mc["stats"]["iters"],
+                      "phase_ms": {"assemble": mc["stats"]["asm"], "prec_init": mc["stats"]["prec"],
+                                   "solve": mc["stats"]["sol"]},
+                      "e2e": {"value": mc["e2e"], "unit": "ms/step", "h2d_bytes_per_step": mc["h2d"],
+                              "d2h_bytes_per_step": mc["d2h"], "same_steps_as_value": True},
+                      "cd": float(mc["forces"][2]), "cl": float(mc["forces"][3]), "gpu_launches": int(mc["launches"]),
+                      "caveat": f"L2-resident: the matrices hold {mat_mb:.0f} MB < 126 MB of L2; launch- and "
+                                f"latency-bound, no roofline is quoted for it",
+                      "paired_with": "bench.py --impl reference (same mesh, parameters and step count on the host cores)"}
+        c3.close()
     if not a.no_cpu_baseline and world == 1:
+        # bounded CPU sample on the same box: all cores (partitioned) and one thread, both measured on C3
         threads = os.cpu_count() or 1
-        ms, n_s, it = cpu_reference_run(pkg, a.mesh, a.cpu_h, 1, 1, threads)
+        par = cpu_arm(pkg, a.cpu_mesh, a.cpu_h, 3, 1, threads, budget_s=60.0)
+        ser = cpu_arm(pkg, a.cpu_mesh, a.cpu_h, 1, 1, 1, budget_s=60.0, serial=True)
         line["cpu_baseline"] = {
-            "value": ms * N / n_s, "unit": "ms/step", "cores": threads, "kind": "port",
-            "sample": (f"oracle on {a.mesh} h={a.cpu_h} ({n_s} DoFs): {ms:.0f} ms/step measured ({it:.0f} GMRES its), "
-                       f"scaled linearly in DoFs to {N}; assembly on {threads} threads, solve serial")}
-    L.nsb_free_pinned(pin_bc)
-    L.nsb_free_pinned(pin_sol)
+            "value": par["ms_per_step"], "unit": "ms/step", "cores": threads, "kind": "port",
+            "sample": (f"{CPU_ARM_TEXT} on C3 ({a.cpu_mesh} h={a.cpu_h}, {par['n_dofs']} DoFs), NOT on the headline mesh: "
+                       f"{par['steps_timed']} steps after 1 warm-up step as `mpirun -n {threads}` runs it (one subdomain per "
+                       f"core, rank-local ILU(0)): {par['ms_per_step']:.0f} ms/step, {par['gmres_iters_per_step']:.1f} GMRES "
+                       f"its; single thread: {ser['ms_per_step']:.0f} ms/step ({ser['steps_timed']} step). Compare with `c3`, "
+                       f"not with `value`"),
+            "single_thread_ms_per_step": ser["ms_per_step"], "all_cores_phase_ms": par["phase_ms"],
+            "single_thread_phase_ms": ser["phase_ms"], "config": {"mesh": a.cpu_mesh, "h": a.cpu_h, "n_dofs": par["n_dofs"]},
+            "native_same_config_ms_per_step": line.get("c3", {}).get("ms_per_step"),
+            # labelled extrapolation, never used as a value: linear in DoFs ignores the growth of the GMRES and
+            # ILU costs with the mesh, so it is a LOWER bound of the CPU time on the headline mesh
+            "extrapolated_to_headline": {"extrapolated": True, "ms_per_step_lower_bound": par["ms_per_step"] * N / par["n_dofs"],
+                                         "how": "all-cores figure x (headline DoFs / C3 DoFs)"}}
     print(json.dumps(line), flush=True)
     if dist is not None:
-        barrier()
-        dev.close()
         dist.destroy_process_group()
     return 0
 

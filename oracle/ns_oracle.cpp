@@ -5,6 +5,7 @@
 // /root/reference/src/NavierStokes.cpp unless another file is named) or the
 // SURVEY.md appendix that restates the deal.II / Trilinos semantics.
 #include "ns_oracle.h"
+#include "ns_oracle_internal.h"
 
 #include <algorithm>
 #include <array>
@@ -17,27 +18,6 @@
 #include <vector>
 
 namespace {
-
-typedef std::vector<double> Vec;
-
-struct CsrMat {
-  int64_t n_rows = 0, n_cols = 0;
-  std::vector<int64_t> rowptr;
-  std::vector<uint32_t> colind;
-  std::vector<double> val;
-  int64_t find(int64_t r, uint32_t c) const {
-    auto b = colind.begin() + rowptr[r], e = colind.begin() + rowptr[r + 1];
-    auto it = std::lower_bound(b, e, c);
-    return (it != e && *it == c) ? it - colind.begin() : -1;
-  }
-  void vmult(double *y, const double *x) const {  // Epetra row-wise CSR product
-    for (int64_t r = 0; r < n_rows; ++r) {
-      double s = 0;
-      for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) s += val[k] * x[colind[k]];
-      y[r] = s;
-    }
-  }
-};
 
 void pattern_from_rows(CsrMat &A, std::vector<std::vector<uint32_t>> &rows, int64_t n_cols) {
   A.n_rows = (int64_t)rows.size();
@@ -218,11 +198,6 @@ const int TRI_LINES[3][2] = {{0, 1}, {1, 2}, {2, 0}};
 const int TET_LINES[6][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 3}, {2, 3}};
 const int TET_FACES[4][3] = {{0, 1, 2}, {1, 0, 3}, {0, 2, 3}, {2, 1, 3}};
 
-struct Quad {
-  std::vector<std::array<double, 3>> pt;
-  std::vector<double> w;
-};
-
 Quad cell_quadrature(int dim, int rule) {
   Quad q;
   if (dim == 2) {
@@ -308,46 +283,6 @@ void p1_eval(int dim, const double *x, double *psi) {
 }  // namespace
 
 // ==========================================================================
-struct nso {
-  int dim, nv, nl, NN, dpc, nq, nqf, rule;
-  int64_t n_verts, n_cells;
-  std::vector<double> xyz;
-  std::vector<uint32_t> cells;
-  std::vector<uint32_t> bfaces;
-  std::vector<int32_t> bids;
-  // numbering
-  uint32_t n_u = 0, n_p = 0;
-  std::vector<uint32_t> cell_dofs;          // n_cells*dpc, deal.II local order
-  std::vector<std::array<double, 3>> support;  // support point of every dof
-  std::vector<int> local_comp, local_scalar;   // per local dof: component, scalar shape index
-  // boundary faces: (cell, local face, id)
-  struct BFace {
-    uint32_t cell;
-    int lf, id;
-  };
-  std::vector<BFace> bf;
-  // system
-  CsrMat A00, A01, A10, S;
-  Vec rhs, lumped, solution_owned, solution;
-  std::vector<uint32_t> bc_dofs;
-  std::vector<double> bc_vals;
-  // reference tables
-  Quad quad;
-  std::vector<double> wface;
-  std::vector<double> phi;    // nq*NN
-  std::vector<double> dphi;   // nq*NN*3 (reference gradients)
-  std::vector<double> psi;    // nq*nv
-  // parameters (NavierStokes.hpp:254-256, :306)
-  double nu = 1e-3, p_out = 0.0, Diameter = 0.4, deltat = 0.01, alpha = 0.5;
-  int inlet_kind = NSO_INLET_PARABOLIC, inlet_sin = 0, bc_diag_mode = 0;
-  double U_m = 0.3, H = 0.41, inlet_time = 0.0;
-  double outer_rtol = 1e-6, inner_rtol = 1e-2;
-  int n_tmp = 30, max_it = 10000, threads = 1;
-
-  double inlet_value(const double *p, int comp, double t) const;
-  double mean_vel(double t) const;
-};
-
 // InletVelocity::value of the drivers (tests/2D/test_01/src/test_01.cpp:29-36,
 // tests/3D/test_01/src/test_01.cpp:29-36, tests/2D/test_naca/src/test_03.cpp:28-35,
 // tests/2D/test_03/src/test_03.cpp for the sin(pi t/8) factor).
@@ -550,7 +485,10 @@ nso *nso_create(int dim, int64_t n_verts, const double *xyz, int64_t n_cells, co
   return o;
 }
 
-void nso_destroy(nso *o) { delete o; }
+void nso_destroy(nso *o) {
+  if (o) nso_baseline_free(o);
+  delete o;
+}
 
 void nso_sizes(const nso *o, int64_t out[10]) {
   out[0] = o->n_u;
@@ -644,15 +582,6 @@ static void cell_geometry(const nso *o, int64_t c, double Jinv[3][3], double *ab
   *absdet = std::fabs(det);
 }
 
-// Per-cell FEValues data: vector-valued shape values/gradients through the
-// extractors (fe_values[velocity].value / gradient / divergence,
-// fe_values[pressure].value), kept as full tensors -- the reference's triple
-// loop multiplies them out term by term.
-struct CellFE {
-  // [q][i][d], [q][i][d][e] (component d, derivative e), [q][i]
-  std::vector<double> val, grad, div, pval, JxW;
-};
-
 static void reinit_cell(const nso *o, int64_t c, CellFE &fe) {
   const int dim = o->dim, dpc = o->dpc, nq = o->nq, NN = o->NN, nv = o->nv;
   double Jinv[3][3], adet;
@@ -681,8 +610,8 @@ static void reinit_cell(const nso *o, int64_t c, CellFE &fe) {
 }
 
 // reference :171-254: the (q, i, j) triple loop, literally.
-static void cell_contribution(const nso *o, int64_t c, CellFE &fe, double *cell_matrix, double *cell_rhs,
-                              double *cell_lumped) {
+void nso_cell_contribution(const nso *o, int64_t c, CellFE &fe, double *cell_matrix, double *cell_rhs,
+                           double *cell_lumped) {
   const int dim = o->dim, dpc = o->dpc, nq = o->nq;
   reinit_cell(o, c, fe);
   std::fill(cell_matrix, cell_matrix + dpc * dpc, 0.0);
@@ -737,7 +666,7 @@ static void cell_contribution(const nso *o, int64_t c, CellFE &fe, double *cell_
 }
 
 void nso_assemble(nso *o, double time) {
-  const int dim = o->dim, dpc = o->dpc;
+  const int dpc = o->dpc;
   const uint32_t nu_ = o->n_u;
   std::fill(o->A00.val.begin(), o->A00.val.end(), 0.0);  // :154-156
   std::fill(o->A01.val.begin(), o->A01.val.end(), 0.0);
@@ -756,7 +685,7 @@ void nso_assemble(nso *o, double time) {
       CellFE fe;
 #pragma omp for schedule(static)
       for (int64_t b = 0; b < nb; ++b)
-        cell_contribution(o, c0 + b, fe, &M[(size_t)b * dpc * dpc], &R[(size_t)b * dpc], &L[(size_t)b * dpc]);
+        nso_cell_contribution(o, c0 + b, fe, &M[(size_t)b * dpc * dpc], &R[(size_t)b * dpc], &L[(size_t)b * dpc]);
     }
     for (int64_t b = 0; b < nb; ++b) {
       const uint32_t *dofs = &o->cell_dofs[(size_t)(c0 + b) * dpc];
@@ -779,7 +708,13 @@ void nso_assemble(nso *o, double time) {
   }
   for (auto &x : o->lumped) x = o->deltat / x;  // :287-290 (deltat/0 on pressure dofs)
 
-  // ---- Dirichlet boundary conditions, :297-329 ----
+  nso_apply_boundary(o, time);
+}
+
+// ---- Dirichlet boundary conditions, :297-329 ----
+void nso_apply_boundary(nso *o, double time) {
+  const int dim = o->dim, dpc = o->dpc;
+  const uint32_t nu_ = o->n_u;
   o->inlet_time = time;  // :306 inlet_velocity.set_time(time)
   std::map<uint32_t, double> bv;
   auto interpolate = [&](const std::vector<int> &ids, const std::vector<bool> &zero) {

@@ -71,6 +71,16 @@ void nso_vmult(const nso *, const double *x, double *y);
  * serial and in cell order). */
 void nso_set_threads(nso *, int n);
 
+/* ---- CPU baseline mode (bench.py only; ns_baseline.cpp) --------------------------------
+ * The same algorithm the way `mpirun -n P` of the reference runs it, with P OpenMP threads:
+ * cells partitioned into P subdomains (reference :19-23), every subdomain assembles its own
+ * cells (:166), rank-local ILU(0) of the diagonal blocks (Ifpack, overlap 0; :958-959), all
+ * SpMV / dot / axpy of the outer and inner GMRES solves on all threads.  cell_part[c] in
+ * [0, n_parts).  The checker functions above are unaffected. */
+int nso_baseline_partition(nso *, int n_parts, const int32_t *cell_part);
+void nso_baseline_assemble(nso *, double time);
+int nso_baseline_solve_time_step(nso *, int *iters, double *t_prec, double *t_solve);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ _lib = None
 def build():
     """Compiles the oracle (g++) if the shared object is missing or stale."""
     so = os.path.join(_HERE, "libns_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("ns_oracle.cpp", "ns_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("ns_oracle.cpp", "ns_baseline.cpp", "ns_oracle.h", "ns_oracle_internal.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", os.path.dirname(_HERE), "oracle"], stdout=subprocess.DEVNULL)
     return so
@@ -60,6 +60,10 @@ def lib():
         L.nso_compute_forces.argtypes = [p, C.c_double, f64p]
         L.nso_vmult.argtypes = [p, f64p, f64p]
         L.nso_set_threads.argtypes = [p, C.c_int]
+        L.nso_baseline_partition.argtypes = [p, C.c_int, i32p]
+        L.nso_baseline_assemble.argtypes = [p, C.c_double]
+        L.nso_baseline_solve_time_step.argtypes = [p, C.POINTER(C.c_int), f64p, f64p]
+        L.nso_baseline_solve_time_step.restype = C.c_int
         _lib = L
     return _lib
 
@@ -183,6 +187,21 @@ class Oracle:
         y = np.empty(self.N, np.float64)
         self.L.nso_vmult(self.h, _p(x, C.c_double), _p(y, C.c_double))
         return y
+
+    # ---- CPU baseline mode (bench.py only): the algorithm as `mpirun -n P` runs it ----
+    def baseline_partition(self, n_parts, cell_part):
+        cp = np.ascontiguousarray(cell_part, np.int32)
+        assert cp.size == self.n_cells
+        if self.L.nso_baseline_partition(self.h, n_parts, _p(cp, C.c_int32)) != 0:
+            raise ValueError("bad partition")
+
+    def baseline_assemble(self, time):
+        self.L.nso_baseline_assemble(self.h, time)
+
+    def baseline_solve_time_step(self):
+        it, tp, ts = C.c_int(), C.c_double(), C.c_double()
+        rc = self.L.nso_baseline_solve_time_step(self.h, C.byref(it), C.byref(tp), C.byref(ts))
+        return rc, it.value, tp.value, ts.value
 
     def scipy_blocks(self):
         import scipy.sparse as sp
