@@ -1,7 +1,7 @@
 """Thread scaling of the CPU baseline (oracle/ns_baseline.cpp) on BASELINE config C3: the reference algorithm as
 `mpirun -n P` runs it, P = 1 ... all cores, 1 warm-up + 2 timed steps each.  Bench/test infrastructure only.
 
-    python tools/cpu_baseline_scaling.py [P ...]
+    python tests/cpu_baseline_scaling.py [P ...]
 """
 import importlib
 import json
