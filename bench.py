@@ -424,6 +424,12 @@ def main():
     ms_prec = dev.bench_kernel(2, 5)
     ms_schur = dev.bench_kernel(3, 5)
     ms_spmv_can = dev.bench_kernel(0, 10) if (not a.no_canonical_spmv and world == 1) else None
+    parts = {"F_solve": dev.bench_kernel(9, 10), "schur_solve": dev.bench_kernel(10, 10),
+             "block_product": ms_spmv, "cgs2_k14": dev.bench_kernel(13, 10),
+             "B_vec0": dev.bench_kernel(8, 10), "Bt_dst1": dev.bench_kernel(7, 10)}
+    if world > 1:
+        parts["velocity_halo_exchange"] = dev.bench_kernel(11, 20)
+        parts["pressure_allgather"] = dev.bench_kernel(12, 20)
     clocks = sampler.stop()
 
     gb = 1e-9
@@ -463,7 +469,7 @@ def main():
             "spmv_canonical_gbs": (spmv_canonical_bytes(info) * gb / (ms_spmv_can * 1e-3)) if ms_spmv_can else None,
             "spmv_canonical_ms": ms_spmv_can,
             "spmv_canonical_frac_of_hbm": (spmv_canonical_bytes(info) * gb / (ms_spmv_can * 1e-3) / hbm_peak) if ms_spmv_can else None,
-            "prec_apply_ms": ms_prec, "cd": float(forces[2]), "cl": float(forces[3]),
+            "prec_apply_ms": ms_prec, "iteration_parts_ms": parts, "cd": float(forces[2]), "cl": float(forces[3]),
             "rank_count_invariants": dict(m["checks"], cd=float(forces[2]), cl=float(forces[3]),
                                           note="state after the timed steps; equal across --gpus N up to the GMRES tolerance"),
             "setup_s": run.t_setup, "device_bytes": info["device_bytes"],

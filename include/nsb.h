@@ -130,7 +130,10 @@ int nsb_vmult(nsb_ctx *ctx, const double *x_host, double *y_host);
  * which: 0 block SpMV y=Ax on the canonical (reference) CSR, 1 assembly
  * (zero + cell loop + Dirichlet rows), 2 preconditioner apply, 3 S = B Di Bt,
  * 4 Chebyshev sweep on F (node-block storage), 5 block SpMV on the compressed
- * storage the solver uses, 6 Chebyshev sweep on S, 7 dst0 = vec0 - Di .* (A01 p), 8 vec1 = src1 - A10 u.
+ * storage the solver uses, 6 Chebyshev sweep on S, 7 dst0 = vec0 - Di .* (A01 p), 8 vec1 = src1 - A10 u,
+ * 9 the whole F solve of one preconditioner application, 10 the whole Schur solve (incl. its exchanges on
+ * several GPUs), 11 one velocity halo exchange, 12 one all-gather of the owned pressure rows, 13 one CGS2
+ * orthogonalisation against 14 basis vectors.
  * Add 0x100 to flush L2 between repetitions. */
 int nsb_bench_kernel(nsb_ctx *ctx, int which, int reps, double *ms_mean);
 /* CUDA-event bracket on the context's stream: everything the calls in between enqueue, including the gaps the

@@ -67,7 +67,10 @@ struct HostCoarsening {
 // Greedy aggregation on the strength graph, visiting rows in index order; a
 // root takes its (up to max_agg-1) strongest still-free strong neighbours; a
 // row whose strong neighbours are all taken joins its strongest neighbour.
-inline HostCoarsening coarsen(const HostCsr &M, double theta, int max_agg) {
+// owner (optional, n entries, non-decreasing): aggregates never mix rows of different owners, so on
+// several GPUs every coarse row is the sum of fine rows of ONE rank and -- rows being visited in index
+// order -- every rank's aggregates get a contiguous range of coarse ids.
+inline HostCoarsening coarsen(const HostCsr &M, double theta, int max_agg, const int32_t *owner = nullptr) {
   const int64_t n = M.n;
   HostCoarsening C;
   std::vector<double> diag(n, 0.0);
@@ -85,6 +88,7 @@ inline HostCoarsening coarsen(const HostCsr &M, double theta, int max_agg) {
     for (int64_t k = M.rowptr[i]; k < M.rowptr[i + 1]; ++k) {
       const uint32_t j = M.colind[k];
       if (j == (uint32_t)i) continue;
+      if (owner && owner[j] != owner[i]) continue;
       const double w = std::fabs(M.val[k]);
       if (w < theta * std::sqrt(diag[i] * diag[j])) continue;
       if (C.agg[j] == UINT32_MAX)

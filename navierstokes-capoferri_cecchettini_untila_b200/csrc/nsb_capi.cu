@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "forces.cuh"
 #include "krylov.cuh"
+#include "p2p.cuh"
 #include "slab.cuh"
 #include "spmv.cuh"
 
@@ -107,6 +108,19 @@ struct nsb_ctx {
   DevBuf<uint32_t> send_idx;
   DevBuf<double> send_buf;
   ncclComm_t comm = nullptr;
+  // ---- one-sided exchanges over peer memory (p2p.cuh); NSB_P2P=0 keeps the NCCL calls ----
+  // channels: 0 velocity halo, 1 pressure-vertex halo of the distributed fine level of the Schur solve,
+  //           2 all-gather of the owned pressure rows, 3 all-gather of the owned rows of the first coarse level
+  bool use_p2p = false, dist_schur = false;
+  DevBuf<char> arena;
+  std::vector<void *> peer_arena;        // per rank, IPC-mapped (nullptr for this rank)
+  std::vector<int64_t> peer_stage_off;   // [rank*4 + channel]: byte offset of the staging inside that rank's arena
+  std::vector<int64_t> peer_stage_cap;   // [rank*4 + channel]: doubles per parity
+  DevBuf<P2PState> p2p_state;            // 4
+  P2PChannel chan[4];
+  std::vector<int64_t> h_rps;            // host copy of the pattern of S until finalize (vertex halo lists)
+  std::vector<uint32_t> h_cis;
+  std::vector<uint32_t> c_offsets;       // owned ranges of the first coarse level of the Schur hierarchy
   DevBuf<double> a10t;  // A10^T values on the pattern of A01
   // ---- Schur solve: 0 = single-level Chebyshev polynomial, 1 = multilevel V-cycle (amg.cuh) ----
   int schur_mode = 1, amg_nu = 1, amg_max_agg = 8, amg_cycles = 1, amg_coarse_sweeps = 16;
@@ -167,6 +181,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -191,6 +206,7 @@ NcclApi &nccl() {
   api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
   api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
   api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+  api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
   api.Send = (decltype(api.Send))sym("ncclSend");
   api.Recv = (decltype(api.Recv))sym("ncclRecv");
   api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
@@ -210,11 +226,33 @@ void allreduce_sum(nsb_ctx *c, double *buf, size_t count) {
   NSB_NCCL(nccl().AllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->stream));
 }
 
+// ---- one exchange on channel ch (p2p.cuh) ----
+// push: the entries of the send list are x[width * (send_idx ? send_idx[i] : send_base + i) + c]
+void p2p_push(nsb_ctx *c, int ch, int width, int64_t send_base, const double *x) {
+  P2PChannel &C = c->chan[ch];
+  const int64_t total = C.n_send * width;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 2 * kNumSM));
+  NSB_LAUNCH(c, p2p_push_kernel, grid, 256, C.args, width, C.send_idx, send_base, x);
+}
+// unpack: staging entry j -> y[width * (recv_idx ? recv_idx[j] : recv_base + j) + c]
+void p2p_unpack(nsb_ctx *c, int ch, int width, int64_t recv_base, int64_t n_entries, int64_t skip_begin,
+                int64_t skip_end, double *y) {
+  P2PChannel &C = c->chan[ch];
+  const int64_t total = n_entries * width;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 2 * kNumSM));
+  NSB_LAUNCH(c, p2p_unpack_kernel, grid, 256, C.args, width, C.recv_idx, recv_base, n_entries, skip_begin, skip_end, y);
+}
+
 // Refresh the velocity ghosts of x from their owners (Epetra Import of the
 // reference's vmult; `solution = solution_owned`, reference :395).
 void halo_exchange(nsb_ctx *c, double *x) {
   if (c->nranks == 1 || c->neighbors.empty()) return;
   const int d = c->dim;
+  if (c->use_p2p) {
+    p2p_push(c, 0, d, 0, x);
+    p2p_unpack(c, 0, d, (int64_t)c->n_own_nodes, (int64_t)c->n_ghost_nodes, 0, 0, x);
+    return;
+  }
   const int64_t ns = c->send_ptr.back();
   if (ns > 0)
     NSB_LAUNCH(c, halo_pack_kernel, blocks_for(ns * d), 256, ns, d, c->send_idx.p, x, c->send_buf.p);
@@ -232,12 +270,226 @@ void halo_exchange(nsb_ctx *c, double *x) {
 // Make a pressure vector whose owned rows were just computed identical on all ranks.
 void allgather_p(nsb_ctx *c, double *yp) {
   if (c->nranks == 1) return;
+  if (c->use_p2p) {
+    p2p_push(c, 2, 1, (int64_t)c->p_begin, yp);
+    p2p_unpack(c, 2, 1, 0, (int64_t)c->n_p, (int64_t)c->p_begin, (int64_t)c->p_begin + c->n_p_own, yp);
+    return;
+  }
   NSB_NCCL(nccl().GroupStart());
   for (int r = 0; r < c->nranks; ++r) {
     const size_t cnt = c->p_offsets[r + 1] - c->p_offsets[r];
     if (cnt) NSB_NCCL(nccl().Broadcast(yp + c->p_offsets[r], yp + c->p_offsets[r], cnt, ncclDouble, r, c->comm, c->stream));
   }
   NSB_NCCL(nccl().GroupEnd());
+}
+
+// distributed fine level of the Schur solve: refresh the ghost vertices of a pressure-like vector
+void halo_p(nsb_ctx *c, double *z) {
+  if (!c->chan[1].args.n_peers) return;
+  p2p_push(c, 1, 1, 0, z);
+  p2p_unpack(c, 1, 1, 0, c->chan[1].n_recv, 0, 0, z);
+}
+// replicate the first coarse level's right-hand side from the ranks that own its rows
+void allgather_c(nsb_ctx *c, double *bc) {
+  const int64_t b = c->c_offsets[c->rank], e = c->c_offsets[c->rank + 1];
+  p2p_push(c, 3, 1, b, bc);
+  p2p_unpack(c, 3, 1, 0, (int64_t)c->c_offsets[c->nranks], b, e, bc);
+}
+
+// ---- peer-memory exchanges: arena, IPC handles, channel descriptions (p2p.cuh) ----
+struct P2PBlob {  // what every rank publishes (all-gathered once through NCCL)
+  cudaIpcMemHandle_t handle;
+  int64_t stage_off[4], stage_cap[4];
+  int64_t recv_off[2][kP2PMaxPeers];  // channel 0/1: first entry of sender s inside my staging (-1: not a peer)
+};
+
+void p2p_fill_common(nsb_ctx *c, int ch, const std::vector<int> &peers, const std::vector<int64_t> &send_ptr,
+                     const std::vector<int64_t> &peer_off) {
+  P2PChannel &C = c->chan[ch];
+  P2PArgs &a = C.args;
+  a = P2PArgs{};
+  a.n_peers = (int)peers.size();
+  const int nr = c->nranks;
+  for (int k = 0; k < a.n_peers; ++k) {
+    const int r = peers[k];
+    a.peer_rank[k] = r;
+    a.send_ptr[k] = send_ptr[k];
+    char *base = (char *)c->peer_arena[r];
+    a.peer_stage[k] = (double *)(base + c->peer_stage_off[(size_t)r * 4 + ch]);
+    a.peer_cap[k] = c->peer_stage_cap[(size_t)r * 4 + ch];
+    a.peer_off[k] = peer_off[k];
+    a.peer_flag[k] = (unsigned long long *)base + (size_t)ch * nr + c->rank;
+  }
+  a.send_ptr[a.n_peers] = send_ptr[a.n_peers];
+  a.my_flags = (const unsigned long long *)c->arena.p + (size_t)ch * nr;
+  a.my_stage = (const double *)(c->arena.p + c->peer_stage_off[(size_t)c->rank * 4 + ch]);
+  a.my_cap = c->peer_stage_cap[(size_t)c->rank * 4 + ch];
+  a.state = c->p2p_state.p + ch;
+  C.n_send = send_ptr[a.n_peers];
+  C.ready = true;
+}
+
+void p2p_setup(nsb_ctx *c) {
+  c->use_p2p = false;
+  c->dist_schur = false;
+  if (c->nranks == 1) return;
+  const char *env = std::getenv("NSB_P2P");
+  if ((env && std::atoi(env) == 0) || c->nranks > kP2PMaxPeers) return;
+  const int nr = c->nranks, me = c->rank, d = c->dim;
+  // --- pressure-vertex halo of the owned rows of S (pattern replicated: every rank derives all lists) ---
+  std::vector<std::vector<uint32_t>> vsend(nr), vrecv(nr);
+  const bool have_s = !c->h_rps.empty();
+  if (have_s) {
+    const uint32_t b = c->p_begin, e = c->p_begin + c->n_p_own;
+    auto owner_of = [&](uint32_t v) {
+      return (int)(std::upper_bound(c->p_offsets.begin(), c->p_offsets.end(), v) - c->p_offsets.begin()) - 1;
+    };
+    {  // ghosts of my rows
+      std::vector<uint32_t> g;
+      for (int64_t k = c->h_rps[b]; k < c->h_rps[e]; ++k)
+        if (c->h_cis[k] < b || c->h_cis[k] >= e) g.push_back(c->h_cis[k]);
+      std::sort(g.begin(), g.end());
+      g.erase(std::unique(g.begin(), g.end()), g.end());
+      for (uint32_t v : g) vrecv[owner_of(v)].push_back(v);
+    }
+    std::vector<int> stamp(c->n_p_own, -1);
+    for (int r = 0; r < nr; ++r) {  // my vertices that rank r needs
+      if (r == me) continue;
+      for (int64_t k = c->h_rps[c->p_offsets[r]]; k < c->h_rps[c->p_offsets[r + 1]]; ++k) {
+        const uint32_t v = c->h_cis[k];
+        if (v >= b && v < e && stamp[v - b] != r) {
+          stamp[v - b] = r;
+          vsend[r].push_back(v);
+        }
+      }
+      std::sort(vsend[r].begin(), vsend[r].end());
+    }
+  }
+  std::vector<int> vpeers;
+  std::vector<int64_t> vsend_ptr{0}, vrecv_ptr{0};
+  std::vector<uint32_t> vsend_idx, vrecv_idx;
+  for (int r = 0; r < nr; ++r)
+    if (!vsend[r].empty() || !vrecv[r].empty()) {
+      vpeers.push_back(r);
+      vsend_idx.insert(vsend_idx.end(), vsend[r].begin(), vsend[r].end());
+      vrecv_idx.insert(vrecv_idx.end(), vrecv[r].begin(), vrecv[r].end());
+      vsend_ptr.push_back((int64_t)vsend_idx.size());
+      vrecv_ptr.push_back((int64_t)vrecv_idx.size());
+    }
+  // --- arena: [4 x nranks flags][staging of the 4 channels, two parities each] ---
+  P2PBlob mine{};
+  const int64_t cap[4] = {(int64_t)c->n_ghost_nodes * d, (int64_t)vrecv_idx.size(), (int64_t)c->n_p, (int64_t)c->n_p};
+  int64_t off = ((int64_t)4 * nr * 8 + 255) / 256 * 256;
+  for (int ch = 0; ch < 4; ++ch) {
+    mine.stage_off[ch] = off;
+    mine.stage_cap[ch] = cap[ch];
+    off += (2 * cap[ch] * 8 + 255) / 256 * 256;
+  }
+  for (int s = 0; s < kP2PMaxPeers; ++s) mine.recv_off[0][s] = mine.recv_off[1][s] = -1;
+  for (size_t k = 0; k < c->neighbors.size(); ++k) mine.recv_off[0][c->neighbors[k]] = c->recv_ptr[k];
+  for (size_t k = 0; k < vpeers.size(); ++k) mine.recv_off[1][vpeers[k]] = vrecv_ptr[k];
+  c->arena.alloc((size_t)off, &c->dev_bytes);
+  c->arena.zero(c->stream);
+  c->p2p_state.alloc(4, &c->dev_bytes);
+  c->p2p_state.zero(c->stream);
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  if (cudaIpcGetMemHandle(&mine.handle, c->arena.p) != cudaSuccess) {
+    cudaGetLastError();
+    return;  // no IPC here: the NCCL path stays in use
+  }
+  // --- publish (the all-gather doubles as the barrier after which peers may write the zeroed flags) ---
+  DevBuf<char> sendb, recvb;
+  sendb.upload((const char *)&mine, sizeof(P2PBlob), c->stream);
+  recvb.alloc(sizeof(P2PBlob) * (size_t)nr);
+  NSB_NCCL(nccl().AllGather(sendb.p, recvb.p, sizeof(P2PBlob), ncclChar, c->comm, c->stream));
+  std::vector<P2PBlob> all((size_t)nr);
+  recvb.download((char *)all.data(), c->stream);
+  c->peer_arena.assign(nr, nullptr);
+  c->peer_stage_off.assign((size_t)nr * 4, 0);
+  c->peer_stage_cap.assign((size_t)nr * 4, 0);
+  int ok = 1;
+  for (int r = 0; r < nr; ++r) {
+    for (int ch = 0; ch < 4; ++ch) {
+      c->peer_stage_off[(size_t)r * 4 + ch] = all[r].stage_off[ch];
+      c->peer_stage_cap[(size_t)r * 4 + ch] = all[r].stage_cap[ch];
+    }
+    if (r == me) {
+      c->peer_arena[r] = c->arena.p;
+      continue;
+    }
+    if (cudaIpcOpenMemHandle(&c->peer_arena[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      c->peer_arena[r] = nullptr;
+      ok = 0;
+    }
+  }
+  {  // all ranks take the same path: p2p only if every mapping succeeded everywhere
+    DevBuf<double> flag;
+    const double v = ok ? 0.0 : 1.0;
+    flag.upload(&v, 1, c->stream);
+    NSB_NCCL(nccl().AllReduce(flag.p, flag.p, 1, ncclDouble, ncclSum, c->comm, c->stream));
+    double tot = 0;
+    flag.download(&tot, c->stream);
+    if (tot != 0.0) return;
+  }
+  // --- channel 0: velocity halo (lists from nsb_set_halo) ---
+  {
+    std::vector<int> peers(c->neighbors.begin(), c->neighbors.end());
+    std::vector<int64_t> po;
+    for (int r : peers) {
+      if (all[r].recv_off[0][me] < 0) throw ArgError("halo lists are not symmetric between ranks");
+      po.push_back(all[r].recv_off[0][me]);
+    }
+    p2p_fill_common(c, 0, peers, c->send_ptr, po);
+    c->chan[0].send_idx = c->send_idx.p;  // the list of nsb_set_halo
+    c->chan[0].n_recv = c->n_ghost_nodes;
+  }
+  // --- channel 1: pressure-vertex halo ---
+  if (have_s) {
+    std::vector<int64_t> po;
+    for (int r : vpeers) {
+      if (all[r].recv_off[1][me] < 0 && !vsend[r].empty()) throw ArgError("vertex halo lists are not symmetric");
+      po.push_back(std::max<int64_t>(0, all[r].recv_off[1][me]));
+    }
+    p2p_fill_common(c, 1, vpeers, vsend_ptr, po);
+    c->chan[1].own_send_idx.upload(vsend_idx.data(), vsend_idx.size(), c->stream, &c->dev_bytes);
+    c->chan[1].own_recv_idx.upload(vrecv_idx.data(), vrecv_idx.size(), c->stream, &c->dev_bytes);
+    c->chan[1].send_idx = c->chan[1].own_send_idx.p;
+    c->chan[1].recv_idx = c->chan[1].own_recv_idx.p;
+    c->chan[1].n_recv = (int64_t)vrecv_idx.size();
+  }
+  // --- channel 2: all-gather of the owned pressure rows (every other rank is a peer) ---
+  {
+    std::vector<int> peers;
+    std::vector<int64_t> sp{0}, po;
+    for (int r = 0; r < nr; ++r)
+      if (r != me) {
+        peers.push_back(r);
+        sp.push_back(sp.back() + (int64_t)c->n_p_own);
+        po.push_back((int64_t)c->p_begin);
+      }
+    p2p_fill_common(c, 2, peers, sp, po);
+    c->chan[2].n_recv = c->n_p;
+  }
+  NSB_CUDA(cudaStreamSynchronize(c->stream));
+  c->h_rps = {};
+  c->h_cis = {};
+  c->use_p2p = true;
+}
+
+// channel 3 (all-gather of the owned rows of the first coarse Schur level) once the hierarchy exists
+void p2p_setup_coarse(nsb_ctx *c) {
+  std::vector<int> peers;
+  std::vector<int64_t> sp{0}, po;
+  const int64_t mine = (int64_t)c->c_offsets[c->rank + 1] - c->c_offsets[c->rank];
+  for (int r = 0; r < c->nranks; ++r)
+    if (r != c->rank) {
+      peers.push_back(r);
+      sp.push_back(sp.back() + mine);
+      po.push_back((int64_t)c->c_offsets[c->rank]);
+    }
+  p2p_fill_common(c, 3, peers, sp, po);
+  c->chan[3].n_recv = c->c_offsets[c->nranks];
 }
 
 // lanes per CSR row.  Measured on B200 (9.7 M DoFs): S (53 entries per row) 8 lanes 0.078 ms, 16 lanes 0.092;
@@ -248,12 +500,15 @@ int pick_L(const CsrDev &A) {
 }
 
 // y = A x (mode 0), w - A x (1), w - d.*(A x) (2), d.*(A x) (3)
-void spmv(nsb_ctx *c, const CsrDev &A, int mode, const double *x, const double *w, const double *d, double *y) {
+// row0 / n_loc: only rows [row0, row0 + n_loc) (default: all); w, d, y are indexed by the row of A
+void spmv(nsb_ctx *c, const CsrDev &A, int mode, const double *x, const double *w, const double *d, double *y,
+          int64_t row0 = 0, int64_t n_loc = -1) {
   const int L = pick_L(A);
-  const unsigned grid = blocks_for(A.n_rows * L);
-  if (!A.n_rows) return;
+  if (n_loc < 0) n_loc = A.n_rows;
+  const unsigned grid = blocks_for(n_loc * L);
+  if (!n_loc) return;
 #define NSB_SPMV_CASE(LL, MM) \
-  if (L == LL && mode == MM) NSB_LAUNCH(c, (spmv_kernel<LL, MM>), grid, 256, A.view(), x, w, d, y)
+  if (L == LL && mode == MM) NSB_LAUNCH(c, (spmv_kernel<LL, MM>), grid, 256, A.view(), row0, n_loc, x, w, d, y)
 #define NSB_SPMV_L(LL) NSB_SPMV_CASE(LL, 0); NSB_SPMV_CASE(LL, 1); NSB_SPMV_CASE(LL, 2); NSB_SPMV_CASE(LL, 3)
   NSB_SPMV_L(4);
   NSB_SPMV_L(8);
@@ -282,13 +537,15 @@ void block_spmv_canonical(nsb_ctx *c, const double *x, double *y) {
 }
 
 void cheb_sweep(nsb_ctx *c, const CsrDev &M, const double *dinv, const double *b, const double *z, double *d,
-                double *znew, double c1, double c2) {
+                double *znew, double c1, double c2, int64_t row0 = 0, int64_t n_loc = -1) {
   const int L = pick_L(M);
-  const unsigned grid = blocks_for(M.n_rows * L);
-  if (L == 4) NSB_LAUNCH(c, cheb_sweep_kernel<4>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
-  if (L == 8) NSB_LAUNCH(c, cheb_sweep_kernel<8>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
-  if (L == 16) NSB_LAUNCH(c, cheb_sweep_kernel<16>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
-  if (L == 32) NSB_LAUNCH(c, cheb_sweep_kernel<32>, grid, 256, M.view(), dinv, b, z, d, znew, c1, c2);
+  if (n_loc < 0) n_loc = M.n_rows;
+  if (!n_loc) return;
+  const unsigned grid = blocks_for(n_loc * L);
+  if (L == 4) NSB_LAUNCH(c, cheb_sweep_kernel<4>, grid, 256, M.view(), row0, n_loc, dinv, b, z, d, znew, c1, c2);
+  if (L == 8) NSB_LAUNCH(c, cheb_sweep_kernel<8>, grid, 256, M.view(), row0, n_loc, dinv, b, z, d, znew, c1, c2);
+  if (L == 16) NSB_LAUNCH(c, cheb_sweep_kernel<16>, grid, 256, M.view(), row0, n_loc, dinv, b, z, d, znew, c1, c2);
+  if (L == 32) NSB_LAUNCH(c, cheb_sweep_kernel<32>, grid, 256, M.view(), row0, n_loc, dinv, b, z, d, znew, c1, c2);
 }
 
 // y_u = F x_u + A01 x_p  [mode 0]  or  y = d .* (F x_u)  [mode 3], on the slab storage of F_s and A01
@@ -667,6 +924,7 @@ void finalize_setup(nsb_ctx *c) {
   dz(c->chzB, c->n_uloc);
   if (c->send_ptr.size() > 1 && c->send_ptr.back() > 0)
     c->send_buf.alloc((size_t)c->send_ptr.back() * c->dim, &c->dev_bytes);
+  p2p_setup(c);
   build_fslab(c);
   if (c->dim == 2)
     NSB_LAUNCH(c, (mass_diag_kernel<2, false>), blocks_for(c->n_cells), 256, c->n_cells, c->xyz.p, c->cell_verts.p,
@@ -778,10 +1036,30 @@ void amg_build(nsb_ctx *c) {
     return &L;
   };
   AmgLevel *L = add_level(M.n);
+  // several GPUs with peer-memory exchanges: the fine level is distributed over the ranks' owned rows
+  const bool want_dist = c->use_p2p && c->nranks > 1 && c->amg_cycles == 1;
+  std::vector<int32_t> owner;
+  if (want_dist) {
+    owner.resize((size_t)M.n);
+    for (int r = 0; r < c->nranks; ++r)
+      for (uint32_t v = c->p_offsets[r]; v < c->p_offsets[r + 1]; ++v) owner[v] = r;
+  }
+  c->dist_schur = false;
   while (M.n > 64 && c->amg.size() < 16) {
     // the threshold is halved per level: Galerkin coarse operators have relatively weaker couplings
-    HostCoarsening C = coarsen(M, c->amg_theta * std::pow(0.5, (double)(c->amg.size() - 1)), c->amg_max_agg);
+    const bool fine = c->amg.size() == 1;
+    HostCoarsening C = coarsen(M, c->amg_theta * std::pow(0.5, (double)(c->amg.size() - 1)), c->amg_max_agg,
+                               fine && want_dist ? owner.data() : nullptr);
     if (C.coarse.n >= 0.9 * M.n) break;  // coarsening stalled
+    if (fine && want_dist) {
+      c->c_offsets.assign((size_t)c->nranks + 1, (uint32_t)C.coarse.n);
+      for (int r = c->nranks - 1; r >= 0; --r)  // a rank's first row is always a root (see coarsen)
+        c->c_offsets[r] = c->p_offsets[r] < c->p_offsets[r + 1] ? C.agg[c->p_offsets[r]] : c->c_offsets[r + 1];
+      for (int r = 0; r < c->nranks; ++r)
+        if (c->c_offsets[r] > c->c_offsets[r + 1]) throw StructError("Schur hierarchy: coarse rows are not grouped by rank");
+      p2p_setup_coarse(c);
+      c->dist_schur = true;
+    }
     L->agg.upload(C.agg.data(), C.agg.size(), c->stream, &c->dev_bytes);
     L->agg_ptr.upload(C.agg_ptr.data(), C.agg_ptr.size(), c->stream, &c->dev_bytes);
     L->agg_idx.upload(C.agg_idx.data(), C.agg_idx.size(), c->stream, &c->dev_bytes);
@@ -816,24 +1094,29 @@ void amg_numeric(nsb_ctx *c) {
 
 // k Chebyshev-Jacobi sweeps on M z = b.  z_init == nullptr: zero initial guess;
 // otherwise z_init must be za or zb.  Returns the buffer that holds the result.
+// row0 / n_loc (distributed fine level of the Schur solve): only the rank's owned rows are swept and the
+// ghost vertices of the iterate are refreshed before every product.
 double *cheb_smooth(nsb_ctx *c, const CsrDev &M, const double *dinv, const double *b, double *z_init, double *za,
-                    double *zb, double *d, int k, double lmax, double ratio) {
-  const int64_t n = M.n_rows;
+                    double *zb, double *d, int k, double lmax, double ratio, int64_t row0 = 0, int64_t n_loc = -1) {
+  const bool dist = n_loc >= 0;
+  const int64_t n = dist ? n_loc : M.n_rows;
   const double lmin = lmax / ratio, theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   double *z, *zn;
   if (!z_init) {
     z = za;
     zn = zb;
-    NSB_LAUNCH(c, cheb_first_kernel, blocks_for(n), 256, n, dinv, b, 1.0 / theta, d, z);
+    if (n) NSB_LAUNCH(c, cheb_first_kernel, blocks_for(n), 256, n, dinv + row0, b + row0, 1.0 / theta, d + row0, z + row0);
   } else {
     z = z_init == za ? zb : za;
     zn = z_init;
-    cheb_sweep(c, M, dinv, b, z_init, d, z, 0.0, 1.0 / theta);  // d = Dinv (b - M z)/theta, z = z_init + d
+    if (dist) halo_p(c, z_init);
+    cheb_sweep(c, M, dinv, b, z_init, d, z, 0.0, 1.0 / theta, row0, n_loc);  // d = Dinv (b - M z)/theta, z = z_init + d
   }
   double rho = 1.0 / sigma;
   for (int i = 1; i < k; ++i) {
     const double rho_new = 1.0 / (2.0 * sigma - rho);
-    cheb_sweep(c, M, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta);
+    if (dist) halo_p(c, z);
+    cheb_sweep(c, M, dinv, b, z, d, zn, rho_new * rho, 2.0 * rho_new / delta, row0, n_loc);
     std::swap(z, zn);
     rho = rho_new;
   }
@@ -847,6 +1130,23 @@ double *amg_vcycle(nsb_ctx *c, size_t l, const double *b) {
   const double *dinv = amg_dinv(c, l);
   if (l + 1 == c->amg.size())
     return cheb_smooth(c, M, dinv, b, nullptr, L.z0.p, L.z1.p, L.d.p, c->amg_coarse_sweeps, L.lmax, c->amg_coarse_ratio);
+  if (l == 0 && c->dist_schur) {
+    // Fine level on several GPUs: every rank smooths and restricts its OWNED rows of the (replicated) matrix;
+    // b is valid on the owned rows.  Aggregates do not cross ranks (coarsen(..., owner)), so the owned rows of
+    // the coarse right-hand side are complete and one all-gather replicates them; the coarse levels (12 % of
+    // the rows) stay replicated.  The result is valid on the owned rows.
+    const int64_t r0 = c->p_begin, nl = c->n_p_own;
+    double *z = cheb_smooth(c, M, dinv, b, nullptr, L.z0.p, L.z1.p, L.d.p, c->amg_nu, L.lmax, c->amg_smooth_ratio, r0, nl);
+    halo_p(c, z);
+    spmv(c, M, 1, z, b, nullptr, L.r.p, r0, nl);
+    AmgLevel &Lc = *c->amg[1];
+    const int64_t c0 = c->c_offsets[c->rank], nc = (int64_t)c->c_offsets[c->rank + 1] - c0;
+    if (nc) NSB_LAUNCH(c, restrict_kernel, blocks_for(nc), 256, nc, L.agg_ptr.p + c0, L.agg_idx.p, L.r.p, Lc.b.p + c0);
+    allgather_c(c, Lc.b.p);
+    const double *ec = amg_vcycle(c, 1, Lc.b.p);
+    if (nl) NSB_LAUNCH(c, prolong_add_kernel, blocks_for(nl), 256, nl, L.agg.p + r0, ec, c->amg_omega, z + r0);
+    return cheb_smooth(c, M, dinv, b, z, L.z0.p, L.z1.p, L.d.p, c->amg_nu, L.lmax, c->amg_smooth_ratio, r0, nl);
+  }
   double *z = cheb_smooth(c, M, dinv, b, nullptr, L.z0.p, L.z1.p, L.d.p, c->amg_nu, L.lmax, c->amg_smooth_ratio);
   spmv(c, M, 1, z, b, nullptr, L.r.p);
   AmgLevel &Lc = *c->amg[l + 1];
@@ -964,6 +1264,23 @@ const double *schur_solve(nsb_ctx *c, const double *b) {
   return d1;
 }
 
+// dst_p = factor * S^-1 vec1, replicated on all ranks; vec1 holds this rank's owned rows.
+// Replicated Schur solve: the owned rows of vec1 are all-gathered first.  Distributed fine level
+// (dist_schur): the solve works on owned rows and the scaled result is all-gathered instead.
+void schur_apply(nsb_ctx *c, double factor, double *dst_p) {
+  const int64_t np = c->n_p;
+  if (!c->dist_schur) {
+    allgather_p(c, c->vec1.p);
+    const double *d1 = schur_solve(c, c->vec1.p);
+    NSB_LAUNCH(c, scale_kernel, blocks_for(np), 256, np, factor, d1, dst_p);
+    return;
+  }
+  const double *d1 = schur_solve(c, c->vec1.p);
+  const int64_t r0 = c->p_begin, nl = c->n_p_own;
+  if (nl) NSB_LAUNCH(c, scale_kernel, blocks_for(nl), 256, nl, factor, d1 + r0, dst_p + r0);
+  allgather_p(c, dst_p);
+}
+
 // PreconditionAYosida::vmult, reference :1024-1051, inner solves as in prec_apply:
 //   vec0 ~= F^-1 src0;  vec1 = B vec0 - src1;  dst1 ~= S^-1 vec1;  dst0 = vec0 - F^-1 (Bt dst1)
 void prec_apply_yosida(nsb_ctx *c, const double *src, double *dst) {
@@ -971,9 +1288,8 @@ void prec_apply_yosida(nsb_ctx *c, const double *src, double *dst) {
   cheb_solve_F(c, src, c->vec0.p, c->kF, c->lamF, c->rF);                                          // :1035-1037
   halo_exchange(c, c->vec0.p);
   spmv(c, c->a10, 1, c->vec0.p, src + c->n_uloc + c->p_begin, nullptr, c->vec1.p + c->p_begin);   // src1 - B vec0
-  allgather_p(c, c->vec1.p);
-  const double *d1 = schur_solve(c, c->vec1.p);                                                     // :1042-1044
-  NSB_LAUNCH(c, scale_kernel, blocks_for(np), 256, np, -1.0, d1, dst + c->n_uloc);                  // sign of :1039
+  schur_apply(c, -1.0, dst + c->n_uloc);                                                           // :1042-1044, sign of :1039
+  (void)np;
   g_apply(c, dst + c->n_uloc, nullptr, nullptr, c->eig_w.p);                                        // Bt dst1, :1047
   cheb_solve_F(c, c->eig_w.p, dst, c->kF, c->lamF, c->rF);                                          // :1048
   NSB_LAUNCH(c, axpby_kernel, kRedBlocks, 256, (int64_t)c->n_u, 1.0, c->vec0.p, -1.0, dst);         // :1049
@@ -997,10 +1313,9 @@ void prec_apply(nsb_ctx *c, const double *src, double *dst) {
   // vec1 = src1 - B vec0                                 (:982-983)
   halo_exchange(c, c->vec0.p);
   spmv(c, c->a10, 1, c->vec0.p, src + c->n_uloc + c->p_begin, nullptr, c->vec1.p + c->p_begin);
-  allgather_p(c, c->vec1.p);
   // dst1 ~= S^-1 vec1, then dst1 *= -1/alpha             (:986-990)
-  const double *d1 = schur_solve(c, c->vec1.p);
-  NSB_LAUNCH(c, scale_kernel, blocks_for(np), 256, np, -1.0 / c->alpha, d1, dst + c->n_uloc);
+  schur_apply(c, -1.0 / c->alpha, dst + c->n_uloc);
+  (void)np;
   // dst0 = vec0 - Di .* (Bt dst1)                        (:992-994)
   g_apply(c, dst + c->n_uloc, c->vec0.p, c->di.p, dst);
 }
@@ -1205,6 +1520,9 @@ void nsb_destroy(nsb_ctx *c) {
   if (c->prec_graph) cudaGraphDestroy(c->prec_graph);
   c->prec_exec = nullptr;
   c->prec_graph = nullptr;
+  for (size_t r = 0; r < c->peer_arena.size(); ++r)
+    if ((int)r != c->rank && c->peer_arena[r]) cudaIpcCloseMemHandle(c->peer_arena[r]);
+  c->peer_arena.clear();
   if (c->comm) {
     try {
       nccl().CommDestroy(c->comm);
@@ -1360,6 +1678,10 @@ int nsb_set_pattern(nsb_ctx *c, int block, int64_t n_rows, const int64_t *rowptr
       case NSB_S:
         if (n_rows != np) throw ArgError("S must have n_p rows");
         upload_pattern(c, c->s, np, np, rowptr, colind);
+        if (c->nranks > 1) {  // kept until finalize: the vertex halo lists of the distributed Schur level
+          c->h_rps.assign(rowptr, rowptr + n_rows + 1);
+          c->h_cis.assign(colind, colind + rowptr[n_rows]);
+        }
         break;
       default:
         throw ArgError("nsb_set_pattern: unknown block");
@@ -1523,6 +1845,12 @@ int nsb_solve_time_step(nsb_ctx *c, int *iters, double *t_prec, double *t_solve)
     const int its = gmres_solve(c, tol);  // reference :377
     halo_exchange(c, c->sol.p);           // solution = solution_owned (ghost import), reference :395
     NSB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->use_p2p) {
+      P2PState st[4];
+      c->p2p_state.download(st, c->stream);
+      for (int ch = 0; ch < 4; ++ch)
+        if (st[ch].error) throw NcclError("peer-memory exchange timed out on channel " + std::to_string(ch));
+    }
     auto t2 = std::chrono::high_resolution_clock::now();
     const double tp = std::chrono::duration<double>(t1 - t0).count(), ts = std::chrono::duration<double>(t2 - t1).count();
     c->t_ms[1] = 1e3 * tp;
@@ -1651,6 +1979,15 @@ int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
         case 6: cheb_sweep(c, c->s, c->dis.p, c->vec1.p, c->chz_p.p, c->chd_p.p, c->chz_p2.p, 0.5, 0.5); break;
         case 7: g_apply(c, c->sol.p + c->n_uloc, c->vec0.p, c->di.p, c->tmpN.p); break;
         case 8: spmv(c, c->a10, 1, c->vec0.p, c->rhs.p + c->n_uloc + c->p_begin, nullptr, c->vec1.p + c->p_begin); break;
+        case 9: cheb_solve_F(c, c->rhs.p, c->vec0.p, c->kF, c->lamF, c->rF); break;
+        case 10: schur_apply(c, -1.0 / c->alpha, c->tmpN.p + c->n_uloc); break;
+        case 11: halo_exchange(c, c->vec0.p); break;
+        case 12: allgather_p(c, c->tmpN.p + c->n_uloc); break;
+        case 13:  // one CGS2 orthogonalisation against 14 basis vectors (the mean over a restart cycle of 28)
+          multi_dot(c, c->V.p, c->N, 14, c->tmpN.p, Part::FULL, false, c->hdev.p);
+          multi_axpy_dot(c, c->V.p, c->N, 14, c->hdev.p, -1e-30, c->tmpN.p, c->hdev.p + kMaxDots);
+          multi_axpy(c, c->V.p, c->N, 14, c->hdev.p + kMaxDots, -1e-30, c->tmpN.p, true, c->hdev.p + 2 * kMaxDots);
+          break;
         default: throw ArgError("nsb_bench_kernel: unknown kernel id");
       }
       NSB_CUDA(cudaEventRecord(c->ev1, c->stream));

@@ -74,12 +74,13 @@ __global__ void __launch_bounds__(256) block_spmv_kernel(CsrView a00, CsrView a0
 //   mode 2: y = w - d .* (A x)              (dst0 = vec0 - Di .* (Bt dst1), reference :992-994)
 //   mode 3: y = d .* (A x)                  (power iteration on D^-1 A)
 template <int L, int MODE>
-__global__ void __launch_bounds__(256) spmv_kernel(CsrView A, const double *__restrict__ x,
+__global__ void __launch_bounds__(256) spmv_kernel(CsrView A, int64_t row0, int64_t n_loc, const double *__restrict__ x,
                                                    const double *__restrict__ w, const double *__restrict__ d,
                                                    double *__restrict__ y) {
-  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  // rows [row0, row0 + n_loc) of A (a rank's owned rows of a replicated matrix; the whole matrix otherwise)
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L + row0;
   const int sub = threadIdx.x % L;
-  const bool live = g < A.n_rows;
+  const bool live = g < row0 + n_loc;
   const double s = sub_reduce<L>(live ? row_dot<L>(A, g, x, sub) : 0.0);
   if (sub == 0 && live) {
     if (MODE == 0) y[g] = s;
@@ -94,13 +95,13 @@ __global__ void __launch_bounds__(256) spmv_kernel(CsrView A, const double *__re
 //   dnew = c1 * d + c2 * Dinv .* (b - M z);  znew = z + dnew
 // z and znew are distinct buffers (the product gathers z).
 template <int L>
-__global__ void __launch_bounds__(256) cheb_sweep_kernel(CsrView M, const double *__restrict__ dinv,
-                                                         const double *__restrict__ b, const double *__restrict__ z,
-                                                         double *__restrict__ d, double *__restrict__ znew, double c1,
-                                                         double c2) {
-  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+__global__ void __launch_bounds__(256) cheb_sweep_kernel(CsrView M, int64_t row0, int64_t n_loc,
+                                                         const double *__restrict__ dinv, const double *__restrict__ b,
+                                                         const double *__restrict__ z, double *__restrict__ d,
+                                                         double *__restrict__ znew, double c1, double c2) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L + row0;
   const int sub = threadIdx.x % L;
-  const bool live = g < M.n_rows;
+  const bool live = g < row0 + n_loc;
   const double s = sub_reduce<L>(live ? row_dot<L>(M, g, z, sub) : 0.0);
   if (sub == 0 && live) {
     const double dn = c1 * d[g] + c2 * dinv[g] * (b[g] - s);
