@@ -36,7 +36,7 @@ DRV      := $(PKG)/drivers
 # (2/3) while the driver defines another one: an ODR violation whose outcome depends on inlining
 # (DESIGN.md section 7).  Here the driver's definition is used everywhere.
 DRIVER_BIN := $(DRV)/d2_test_01 $(DRV)/d2_test_02 $(DRV)/d2_test_03 $(DRV)/d2_test_naca \
-              $(DRV)/d3_test_01 $(DRV)/d3_test_02 $(DRV)/d3_test_03 $(DRV)/make_mesh
+              $(DRV)/d3_test_01 $(DRV)/d3_test_02 $(DRV)/d3_test_03 $(DRV)/d2_restart $(DRV)/d3_restart $(DRV)/make_mesh
 FACADE   := $(PKG)/host/NavierStokes.cpp $(PKG)/host/NavierStokes.hpp $(PKG)/host/distribute.hpp $(DRV)/driver_common.hpp
 drivers: $(DRIVER_BIN)
 $(DRV)/d2_%: $(DRV)/d2_%.cpp $(FACADE) $(PKG)/libnsb_host.so $(PKG)/libnsb.so

@@ -425,7 +425,7 @@ def main():
     ms_schur = dev.bench_kernel(3, 5)
     ms_spmv_can = dev.bench_kernel(0, 10) if (not a.no_canonical_spmv and world == 1) else None
     parts = {"F_solve": dev.bench_kernel(9, 10), "schur_solve": dev.bench_kernel(10, 10),
-             "block_product": ms_spmv, "cgs2_k14": dev.bench_kernel(13, 10),
+             "block_product": ms_spmv, "gram_schmidt_k14": dev.bench_kernel(13, 10),
              "B_vec0": dev.bench_kernel(8, 10), "Bt_dst1": dev.bench_kernel(7, 10)}
     if world > 1:
         parts["velocity_halo_exchange"] = dev.bench_kernel(11, 20)
@@ -466,6 +466,9 @@ def main():
             "spmv_gbs": spmv_gbs, "spmv_frac_of_hbm": spmv_gbs / hbm_peak, "spmv_ms": ms_spmv,
             "sweep_F_gbs": sweep_gbs, "sweep_F_ms": ms_sweep, "sweep_S_gbs": sweep_s_gbs, "sweep_S_ms": ms_sweep_s,
             "schur_ms": ms_schur, "sweeps_F": info2["sweeps_F"], "schur_levels": info2["schur_levels"],
+            "gram_schmidt_reorth_passes": info2["reorth_passes"],
+            "exchanges": ("peer memory (IPC-mapped NVLink stores)" if info2["exchange_mode"] & 1 else "NCCL") if world > 1 else "none",
+            "schur_fine_level_distributed": bool(info2["exchange_mode"] & 2),
             "spmv_canonical_gbs": (spmv_canonical_bytes(info) * gb / (ms_spmv_can * 1e-3)) if ms_spmv_can else None,
             "spmv_canonical_ms": ms_spmv_can,
             "spmv_canonical_frac_of_hbm": (spmv_canonical_bytes(info) * gb / (ms_spmv_can * 1e-3) / hbm_peak) if ms_spmv_can else None,

@@ -132,8 +132,8 @@ int nsb_vmult(nsb_ctx *ctx, const double *x_host, double *y_host);
  * 4 Chebyshev sweep on F (node-block storage), 5 block SpMV on the compressed
  * storage the solver uses, 6 Chebyshev sweep on S, 7 dst0 = vec0 - Di .* (A01 p), 8 vec1 = src1 - A10 u,
  * 9 the whole F solve of one preconditioner application, 10 the whole Schur solve (incl. its exchanges on
- * several GPUs), 11 one velocity halo exchange, 12 one all-gather of the owned pressure rows, 13 one CGS2
- * orthogonalisation against 14 basis vectors.
+ * several GPUs), 11 one velocity halo exchange, 12 one all-gather of the owned pressure rows, 13 one Gram-Schmidt
+ * orthogonalisation (two passes) against 14 basis vectors.
  * Add 0x100 to flush L2 between repetitions. */
 int nsb_bench_kernel(nsb_ctx *ctx, int which, int reps, double *ms_mean);
 /* CUDA-event bracket on the context's stream: everything the calls in between enqueue, including the gaps the
@@ -150,8 +150,11 @@ int nsb_timers(const nsb_ctx *ctx, double out_ms[4]);
  *       [12] number of levels of the Schur hierarchy
  *       [13] entries of the slab storage of F_s incl. padding [14] sum of the slab windows (nodes)
  *       [15] number of slabs [16] entries of the slab storage of A01 incl. padding
- *       [17] sum of the pressure windows */
-int nsb_info(const nsb_ctx *ctx, int64_t out[18]);
+ *       [17] sum of the pressure windows
+ *       [18] Gram-Schmidt re-orthogonalisation passes taken so far (third read of the Krylov basis)
+ *       [19] bit 0: halo / all-gather exchanges run over peer memory (else NCCL), bit 1: the fine level of the
+ *            Schur hierarchy is distributed over the ranks */
+int nsb_info(const nsb_ctx *ctx, int64_t out[20]);
 
 /* Host-only check of the slab (windowed sliced-ELL) storage the solver kernels stream F_s from
  * (csrc/slab.cuh): builds the layout from a node-level CSR pattern and evaluates y = (F_s (x) I_dim) x

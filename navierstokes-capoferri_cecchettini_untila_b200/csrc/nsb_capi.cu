@@ -33,7 +33,7 @@ struct nsb_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;  // ev_t*: nsb_timer_start/stop
   std::string err;
-  int64_t dev_bytes = 0, launches = 0;
+  int64_t dev_bytes = 0, launches = 0, reorth_count = 0;  // reorth_count: third Gram-Schmidt passes taken
   // sizes
   int64_t n_verts = 0, n_cells = 0, N = 0;
   uint32_t n_u = 0, n_p = 0;
@@ -682,17 +682,18 @@ void multi_axpy(nsb_ctx *c, const double *V, int64_t ld, int k, const double *co
   }
   if (with_norm) allreduce_sum(c, out_norm2, 1);
 }
-// w += sign * V coef, then out[i] = V_i . w (one read of the basis for both)
+// w += sign * V coef, then out[i] = V_i . w (i < k) and out[k] = w . w of the UPDATED w (one read of the basis
+// for the projection, the second set of inner products and the norm)
 void multi_axpy_dot(nsb_ctx *c, const double *V, int64_t ld, int k, const double *coef, double sign, double *w,
                     double *out) {
   if (k > kOrthoMax) {
     multi_axpy(c, V, ld, k, coef, sign, w, false, nullptr);
-    multi_dot(c, V, ld, k, w, Part::FULL, false, out);
+    multi_dot(c, V, ld, k, w, Part::FULL, true, out);
     return;
   }
   const int64_t nu = c->n_u, np = c->n_p;
-  ortho_launch<1>(c, V, ld, k, coef, sign, w, nu + np, nu + (c->rank == 0 ? np : 0), nu, c->n_uloc - nu, false, out);
-  allreduce_sum(c, out, (size_t)k);
+  ortho_launch<1>(c, V, ld, k, coef, sign, w, nu + np, nu + (c->rank == 0 ? np : 0), nu, c->n_uloc - nu, true, out);
+  allreduce_sum(c, out, (size_t)k + 1);
 }
 
 double norm2_host(nsb_ctx *c, const double *v, Part part) {
@@ -1181,8 +1182,10 @@ void auto_inner(nsb_ctx *c) {
     const double gamma = std::max(1.0, h[0] / h[1]);
     // measured on B200 (3d-cylinder, h = 0.04 ... 0.0125): time per step is flat for degrees within
     // +-2 of 0.55 sqrt(7 gamma); a higher degree buys fewer outer iterations at the same total cost
-    c->kF = std::min(16, std::max(3, (int)std::ceil(0.55 * std::sqrt(7.0 * gamma))));
-    c->rF = std::max(6.0, (c->kF / 1.25) * (c->kF / 1.25));
+    // round 2, 9.7 M DoFs (steps 4-11): degree 7 / 8 / 9 / 10 -> 107 / 97 / 92 / 89 outer iterations and
+    // 459 / 449 / 457 / 472 ms per step; the ratio matters at equal degree (8 with 41: 100 iterations, with 52: 97)
+    c->kF = std::min(16, std::max(3, (int)std::ceil(0.47 * std::sqrt(7.0 * gamma))));
+    c->rF = std::max(6.0, (c->kF / 1.1) * (c->kF / 1.1));
   }
   if (c->schur_mode == 0) {
     if (c->sweepsS > 0) {
@@ -1389,7 +1392,7 @@ int gmres_solve(nsb_ctx *c, double tol) {
   ensure_krylov(c);
   const int64_t N = c->N;
   const int m = c->restart;
-  std::vector<double> H((size_t)(m + 1) * m, 0.0), gamma(m + 1), ci(m), si(m), h(m + 2), h2(m + 2), y(m);
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), gamma(m + 1), ci(m), si(m), h(m + 2), h2(m + 3), y(m);
   double *x = c->sol.p, *b = c->rhs.p, *p = c->tmpN.p, *V = c->V.p, *pz = c->pz.p;
   double *hd = c->hdev.p;
   prec_capture(c);
@@ -1421,16 +1424,29 @@ int gmres_solve(nsb_ctx *c, double tol) {
       block_spmv(c, V + (size_t)j * N, p);
       prec_apply_replay(c);
       dim = j + 1;
-      // CGS2: h = V^T vv; vv -= V h; h2 = V^T vv; vv -= V h2; s = ||vv||
+      // Classical Gram-Schmidt with a MEASURED re-orthogonalisation test (deal.II re-orthogonalises its modified
+      // Gram-Schmidt only when a loss-of-orthogonality estimate asks for it):
+      //   pass 1: h = V^T vv;   pass 2: vv -= V h fused with h2 = V^T vv and s^2 = ||vv||^2 (basis read once);
+      //   pass 3, only if ||h2|| > kReorth ||vv||:  vv -= V h2 fused with the norm, h += h2.
+      // After pass 2 the basis is orthogonal to vv up to ||h2|| / ||vv|| (1e-15 ... 1e-11 in practice).  The level
+      // that is kept follows the requested tolerance (1e-3 of it, between 1e-13 and 1e-9): the reference's 1e-6
+      // stopping rule does not need the third read of the basis that CGS2 always paid (a third of the
+      // orthogonalisation traffic), the 1e-12 parity runs keep it whenever the measured loss exceeds 1e-13.
+      const double kReorth = std::min(1e-9, std::max(1e-13, 1e-3 * c->rtol));
       multi_dot(c, V, N, dim, vv, Part::FULL, false, hd);
       multi_axpy_dot(c, V, N, dim, hd, -1.0, vv, hd + kMaxDots);
-      multi_axpy(c, V, N, dim, hd + kMaxDots, -1.0, vv, true, hd + 2 * kMaxDots);
       NSB_CUDA(cudaMemcpyAsync(h.data(), hd, sizeof(double) * dim, cudaMemcpyDeviceToHost, c->stream));
-      NSB_CUDA(cudaMemcpyAsync(h2.data(), hd + kMaxDots, sizeof(double) * dim, cudaMemcpyDeviceToHost, c->stream));
-      double s2;
-      NSB_CUDA(cudaMemcpyAsync(&s2, hd + 2 * kMaxDots, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      NSB_CUDA(cudaMemcpyAsync(h2.data(), hd + kMaxDots, sizeof(double) * (dim + 1), cudaMemcpyDeviceToHost, c->stream));
       NSB_CUDA(cudaStreamSynchronize(c->stream));
-      for (int i = 0; i < dim; ++i) h[i] += h2[i];
+      double s2 = h2[dim], h2n = 0;
+      for (int i = 0; i < dim; ++i) h2n += h2[i] * h2[i];
+      if (h2n > kReorth * kReorth * s2) {
+        multi_axpy(c, V, N, dim, hd + kMaxDots, -1.0, vv, true, hd + 2 * kMaxDots);
+        NSB_CUDA(cudaMemcpyAsync(&s2, hd + 2 * kMaxDots, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        NSB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < dim; ++i) h[i] += h2[i];
+        ++c->reorth_count;
+      }
       const double s = std::sqrt(s2);
       h[j + 1] = s;
       NSB_LAUNCH(c, scale_kernel, kRedBlocks, 256, N, std::isfinite(1.0 / s) ? 1.0 / s : 1.0, vv,
@@ -1983,10 +1999,9 @@ int nsb_bench_kernel(nsb_ctx *c, int which, int reps, double *ms_mean) {
         case 10: schur_apply(c, -1.0 / c->alpha, c->tmpN.p + c->n_uloc); break;
         case 11: halo_exchange(c, c->vec0.p); break;
         case 12: allgather_p(c, c->tmpN.p + c->n_uloc); break;
-        case 13:  // one CGS2 orthogonalisation against 14 basis vectors (the mean over a restart cycle of 28)
+        case 13:  // one orthogonalisation against 14 basis vectors (the mean over a restart cycle of 28): two passes
           multi_dot(c, c->V.p, c->N, 14, c->tmpN.p, Part::FULL, false, c->hdev.p);
           multi_axpy_dot(c, c->V.p, c->N, 14, c->hdev.p, -1e-30, c->tmpN.p, c->hdev.p + kMaxDots);
-          multi_axpy(c, c->V.p, c->N, 14, c->hdev.p + kMaxDots, -1e-30, c->tmpN.p, true, c->hdev.p + 2 * kMaxDots);
           break;
         default: throw ArgError("nsb_bench_kernel: unknown kernel id");
       }
@@ -2022,7 +2037,7 @@ int nsb_timers(const nsb_ctx *c, double out_ms[4]) {
   for (int i = 0; i < 4; ++i) out_ms[i] = c->t_ms[i];
   return NSB_OK;
 }
-int nsb_info(const nsb_ctx *c, int64_t out[18]) {
+int nsb_info(const nsb_ctx *c, int64_t out[20]) {
   if (!c) return NSB_EARG;
   out[0] = c->n_u;
   out[1] = c->n_p;
@@ -2042,6 +2057,8 @@ int nsb_info(const nsb_ctx *c, int64_t out[18]) {
   out[15] = c->fslab.n_slabs;
   out[16] = c->gslab.padded;
   out[17] = (int64_t)c->gslab.pwin_list.n;
+  out[18] = c->reorth_count;
+  out[19] = (c->use_p2p ? 1 : 0) | (c->dist_schur ? 2 : 0);
   return NSB_OK;
 }
 

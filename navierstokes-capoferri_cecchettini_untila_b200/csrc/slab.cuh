@@ -38,7 +38,10 @@
 
 namespace nsb {
 
-constexpr int kSlabThreads = 256;  // virtual rows (= threads) per slab
+#ifndef NSB_SLAB_THREADS
+#define NSB_SLAB_THREADS 256
+#endif
+constexpr int kSlabThreads = NSB_SLAB_THREADS;  // virtual rows (= threads) per slab
 constexpr int kSlabSlices = kSlabThreads / 32;
 constexpr int kSlabMaxChunks = 3;
 constexpr uint32_t kVposNone = 0x3ffu;
@@ -316,7 +319,7 @@ __global__ void slab_repack_kernel(int64_t n, const uint32_t *__restrict__ src, 
 // resident CTAs, as prefetching the first batch before the window is staged and as an asynchronous
 // (cp.async) window fill -- 0.34 ms per sweep in all cases; bank-aware entry order: 0.40 -> 0.345 ms.
 constexpr int kSlabBatch = 4;
-constexpr int kSlabMinBlocks = 6;
+constexpr int kSlabMinBlocks = 1536 / kSlabThreads;  // 1536 resident threads per SM (40 registers)
 template <int DIM, int BATCH>
 __device__ __forceinline__ void slab_product(const SlabView &S, int s, const double *__restrict__ x, double *sm,
                                              double (&acc)[DIM]) {

@@ -344,9 +344,9 @@ class Device:
         return out
 
     def info(self):
-        out = (C.c_int64 * 18)()
+        out = (C.c_int64 * 20)()
         self._chk(self.L.nsb_info(self.h, out))
         keys = ["n_u", "n_p", "n_cells", "nnz_a00", "nnz_a01", "nnz_a10", "nnz_s", "n_q", "device_bytes", "sweeps_F",
                 "sweeps_S", "schur_mode", "schur_levels", "slab_entries", "slab_window_total", "slab_count",
-                "gslab_entries", "gslab_window_total"]
+                "gslab_entries", "gslab_window_total", "reorth_passes", "exchange_mode"]
         return dict(zip(keys, [int(v) for v in out]))

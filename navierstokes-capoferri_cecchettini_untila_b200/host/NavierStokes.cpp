@@ -374,6 +374,9 @@ void NavierStokes::export_data(const unsigned int &time_step) {
   const std::string file_name("../cache/state-ns-" + std::to_string(time_step) + ".dat");
   std::ofstream f(file_name, std::fstream::binary);
   f.write(reinterpret_cast<const char *>(rbuf.data()), (std::streamsize)(rbuf.size() * sizeof(double)));
+  f.close();
+  // a checkpoint that cannot be written must not be lost silently: a later solve(time_step) depends on it
+  if (!f) throw std::runtime_error("export_data: cannot write " + file_name);
 }
 
 // reference :787-805

@@ -101,3 +101,84 @@ def test_checkpoint_and_vtu_output(pkg, tmp_path):
     assert st.size == N and np.isfinite(st).all() and np.abs(st).max() > 0.1
     txt = open(tmp_path / "output" / "output-stokes_4.0.vtu").read()
     assert f'NumberOfCells="{s["n_cells"]}"' in txt and 'Name="velocity"' in txt and 'Name="partitioning"' in txt
+
+
+def _restart_driver(base, binary, *args):
+    r = subprocess.run([os.path.join(PKG_DIR, "drivers", binary), "../mesh/domain.msh", *[str(a) for a in args]],
+                       cwd=str(base / "build"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def _csv_rows(path):
+    lines = open(path).read().strip().split("\n")[1:]
+    return np.array([[float(x) for x in l.split(",")] for l in lines])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("binary,mesh_name,h,dim,um", [("d2_restart", "2d-cylinder", 0.05, 2, 0.3),
+                                                       ("d3_restart", "3d-cylinder", 0.1, 3, 0.45)])
+def test_restart_and_post_process(pkg, oracle_mod, tmp_path, binary, mesh_name, h, dim, um):
+    """Restart path of the reference (src/NavierStokes.cpp:457-463, 501-568, 787-805) and post_process
+    (:808-828, src/postprocess.cpp): n steps in one go; a NEW object continues from the checkpoint of step k and
+    must reach the same state and force rows as the uninterrupted run; post_process re-reads the checkpoints
+    and reproduces the Cd of the time loop; the on-disk order of a checkpoint is the first-encounter order of
+    the dofs over the cells (:571-784 on one rank), checked against the oracle's independent numbering."""
+    subprocess.check_call(["make", "-C", ROOT, "drivers"], stdout=subprocess.DEVNULL)
+    n, k = 6, 3
+    for d in ("build", "output", "cache", "mesh"):
+        os.makedirs(tmp_path / d, exist_ok=True)
+    msh = str(tmp_path / "mesh" / "domain.msh")
+    subprocess.check_call([os.path.join(PKG_DIR, "drivers", "make_mesh"), mesh_name, str(h), msh])
+    T = n * 0.01
+    _restart_driver(tmp_path, binary, T, "full")
+    rows_full = _csv_rows(tmp_path / "build" / "forces_vs_time.csv")
+    assert rows_full.shape == (n, 9)
+    states_full = {s: np.fromfile(tmp_path / "cache" / f"state-ns-{s}.dat") for s in range(n + 1)}
+    # --- the on-disk order: file[perm[i]] = solution[i], perm = first encounter over the cells' dof lists ---
+    prob = pkg.Problem.read_msh(msh, dim).build(inlet=(0, um, 0.41, 0))
+    orc = oracle_mod.Oracle(dim, prob.array("xyz"), prob.array("cells"), prob.array("bfaces"), prob.array("bids"))
+    cd = orc.cell_dofs()
+    _, first = np.unique(cd, return_index=True)       # first occurrence of every dof in the cell walk
+    perm = np.empty(orc.N, np.int64)
+    perm[np.argsort(first)] = np.arange(orc.N)        # dof -> rank of its first occurrence
+    dev = pkg.Device(dim).load_problem(prob)
+    nu = prob.mean_velocity(0.0) * 0.4 / 20
+    dev.set_params(0.01, nu)
+    t = 0.0
+    for _ in range(k):
+        t += 0.01
+        dev.assemble(t)
+        dev.solve_time_step()
+    x = dev.solution()
+    expect = np.empty(orc.N)
+    expect[perm] = x
+    # two runs of the same solver at its 1e-6 stopping rule (atomics order differs): agreement far below the O(1)
+    # error of a wrong permutation
+    assert np.linalg.norm(states_full[k] - expect) < 1e-4 * np.linalg.norm(expect)
+    dev.close()
+    # --- post_process over the checkpoints of the full run: same Cd as the time loop printed ---
+    out = _restart_driver(tmp_path, binary, T, "post", 1, n)
+    assert out.count("Importing time step") == n and out.count("Exporting pvtu files") == n
+    cds = [float(l.split("(Cd):")[1].split()[0]) for l in out.split("\n") if "Drag coefficient (Cd):" in l]
+    assert len(cds) == n and np.allclose(cds, rows_full[:, 7], rtol=1e-5)
+    assert os.path.exists(tmp_path / "output" / f"output-stokes_{n}.pvtu")
+    # --- restart: a new object continues from step k ---
+    out = _restart_driver(tmp_path, binary, T, "restart", k)
+    assert f"Continuing execution from time step {k}" in out
+    rows_re = _csv_rows(tmp_path / "build" / "forces_vs_time.csv")
+    assert rows_re.shape == (n - k, 9)
+    assert np.allclose(rows_re[:, 0], rows_full[k:, 0])
+    assert np.allclose(rows_re[:, 5:], rows_full[k:, 5:], rtol=2e-4, atol=1e-7), (rows_re[:, 5:], rows_full[k:, 5:])
+    st = np.fromfile(tmp_path / "cache" / f"state-ns-{n}.dat")
+    assert np.linalg.norm(st - states_full[n]) < 1e-4 * np.linalg.norm(states_full[n])
+    # the imported state is written back unchanged at the restart step (export_data right after import_data)
+    assert np.array_equal(np.fromfile(tmp_path / "cache" / f"state-ns-{k}.dat"), states_full[k])
+
+
+def test_export_data_reports_an_unwritable_checkpoint(pkg, tmp_path):
+    """a failed write of ../cache/state-ns-*.dat must not pass silently (source-level check: the
+    facade tests the stream and throws)."""
+    src = open(os.path.join(PKG_DIR, "host", "NavierStokes.cpp")).read()
+    body = src[src.index("void NavierStokes::export_data"):src.index("void NavierStokes::import_data")]
+    assert "if (!f) throw" in body

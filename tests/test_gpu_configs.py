@@ -6,9 +6,10 @@ against the CPU oracle on the same mesh: solution 1e-8 relative, Cd/Cl 1e-6, bot
 Also the per-entry form of the 1e-10 matrix tolerance: every stored entry is compared relative to
 max(|reference entry|, 1e-3 * largest entry of its row), i.e. small entries next to the M/dt
 diagonal are checked against their own magnitude, not against the block maximum.  A third floor,
-1e-6 * largest entry of the block, covers rows whose exact entries vanish (e.g. the d/dx coupling of
-an edge node whose cells are symmetric in x): there both sides hold only the rounding noise of the
-cancelled summands, ~1e-16 of the block's scale, and no relative statement is possible."""
+1e-5 * largest entry of the block, covers entries that vanish or nearly vanish by cancellation (e.g. the
+d/dx coupling of an edge node whose cells are symmetric in x): there both sides hold the rounding noise
+of summands of the block's scale, a few 1e-16 of it (measured: 3.6e-16), so the statement that can be
+made is absolute: |error| <= 1e-15 * largest entry of the block."""
 import math
 
 import numpy as np
@@ -84,7 +85,7 @@ def test_time_steps_match_oracle_on_driver_configs(pkg, oracle_mod, name):
         dev.set_solution(xo)  # same state for the next assembly
 
 
-def _per_entry_worst(rowptr, got, ref, floor=1e-3, block_floor=1e-6):
+def _per_entry_worst(rowptr, got, ref, floor=1e-3, block_floor=1e-5):
     """max over entries of |got - ref| / max(|ref|, floor * max|row of ref|, block_floor * max|ref|)."""
     n = rowptr.size - 1
     lens = np.diff(rowptr)
