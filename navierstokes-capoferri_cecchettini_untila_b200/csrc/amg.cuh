@@ -48,6 +48,47 @@ __global__ void prolong_add_kernel(int64_t n, const uint32_t *__restrict__ agg, 
   if (i < n) z[i] += omega * ec[agg[i]];
 }
 
+// The coarsest level (<= kCoarseFusedMax rows): all k Chebyshev-Jacobi sweeps of M z = b (zero initial guess,
+// same recurrence as cheb_smooth) in ONE single-CTA launch, the iterate in shared memory -- the 16
+// separate sweep launches of 3-4 us each were a quarter of the V-cycle's time.  One thread per row.
+constexpr int kCoarseFusedMax = 1024;
+__global__ void __launch_bounds__(kCoarseFusedMax) coarse_cheb_kernel(CsrView M, const double *__restrict__ dinv,
+                                                                      const double *__restrict__ b, int k, double lmax,
+                                                                      double ratio, double *__restrict__ z_out) {
+  __shared__ double z[kCoarseFusedMax];
+  const int i = threadIdx.x;
+  const int n = (int)M.n_rows;
+  const double lmin = lmax / ratio, theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  double di = 0, bi = 0, dd = 0, zz = 0;
+  int64_t kb = 0, ke = 0;
+  if (i < n) {
+    di = dinv[i];
+    bi = b[i];
+    kb = M.rowptr[i];
+    ke = M.rowptr[i + 1];
+    dd = di * bi / theta;
+    zz = dd;
+    z[i] = zz;
+  }
+  __syncthreads();
+  double rho = 1.0 / sigma;
+  for (int s = 1; s < k; ++s) {
+    const double rho_new = 1.0 / (2.0 * sigma - rho);
+    double r = bi;
+    if (i < n)
+      for (int64_t q = kb; q < ke; ++q) r -= M.val[q] * z[M.colind[q]];
+    __syncthreads();
+    if (i < n) {
+      dd = rho_new * rho * dd + 2.0 * rho_new / delta * di * r;
+      zz += dd;
+      z[i] = zz;
+    }
+    __syncthreads();
+    rho = rho_new;
+  }
+  if (i < n) z_out[i] = zz;
+}
+
 // ---- host-side setup (runs once) -------------------------------------------
 struct HostCsr {
   int64_t n = 0;

@@ -34,6 +34,12 @@ struct nsb_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;  // ev_t*: nsb_timer_start/stop
   std::string err;
   int64_t dev_bytes = 0, launches = 0, reorth_count = 0;  // reorth_count: third Gram-Schmidt passes taken
+  // NSB_TRACE=<path prefix>: a %globaltimer stamp after every kernel (also inside the captured graph); the last
+  // stamp of every slot is written to <prefix><rank>.csv by nsb_destroy -- the per-kernel timeline of a multi-GPU
+  // run, where ncu cannot be used
+  DevBuf<unsigned long long> trace;
+  std::vector<const char *> trace_name;
+  int64_t trace_pos = 0;
   // sizes
   int64_t n_verts = 0, n_cells = 0, N = 0;
   uint32_t n_u = 0, n_p = 0;
@@ -110,14 +116,15 @@ struct nsb_ctx {
   ncclComm_t comm = nullptr;
   // ---- one-sided exchanges over peer memory (p2p.cuh); NSB_P2P=0 keeps the NCCL calls ----
   // channels: 0 velocity halo, 1 pressure-vertex halo of the distributed fine level of the Schur solve,
-  //           2 all-gather of the owned pressure rows, 3 all-gather of the owned rows of the first coarse level
+  //           2 all-gather of the owned pressure rows, 3 all-gather of the owned rows of the first coarse level,
+  //           4 all-reduce of the Gram-Schmidt inner products / norms (<= kP2PReduceSlot doubles)
   bool use_p2p = false, dist_schur = false;
   DevBuf<char> arena;
   std::vector<void *> peer_arena;        // per rank, IPC-mapped (nullptr for this rank)
-  std::vector<int64_t> peer_stage_off;   // [rank*4 + channel]: byte offset of the staging inside that rank's arena
-  std::vector<int64_t> peer_stage_cap;   // [rank*4 + channel]: doubles per parity
-  DevBuf<P2PState> p2p_state;            // 4
-  P2PChannel chan[4];
+  std::vector<int64_t> peer_stage_off;   // [rank*kP2PChannels + channel]: byte offset of the staging inside that rank's arena
+  std::vector<int64_t> peer_stage_cap;   // [rank*kP2PChannels + channel]: doubles per parity
+  DevBuf<P2PState> p2p_state;            // kP2PChannels
+  P2PChannel chan[kP2PChannels];
   std::vector<int64_t> h_rps;            // host copy of the pattern of S until finalize (vertex halo lists)
   std::vector<uint32_t> h_cis;
   std::vector<uint32_t> c_offsets;       // owned ranges of the first coarse level of the Schur hierarchy
@@ -161,6 +168,12 @@ int guarded(nsb_ctx *c, F &&f) {
 inline unsigned blocks_for(int64_t n_threads, int block = 256) { return (unsigned)((n_threads + block - 1) / block); }
 
 #define NSB_LAUNCH(c, kernel, grid, block, ...) NSB_LAUNCH_SMEM(c, kernel, grid, block, 0, __VA_ARGS__)
+constexpr int64_t kTraceSlots = 8192;
+__global__ void trace_stamp_kernel(unsigned long long *slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  *slot = t;
+}
 #define NSB_LAUNCH_SMEM(c, kernel, grid, block, smem, ...)       \
   do {                                                           \
     kernel<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__); \
@@ -169,6 +182,11 @@ inline unsigned blocks_for(int64_t n_threads, int block = 256) { return (unsigne
     else                                                         \
       ++(c)->launches;                                           \
     NSB_CUDA(cudaGetLastError());                                \
+    if ((c)->trace.p) {                                          \
+      const int64_t slot_ = (c)->trace_pos++ % kTraceSlots;      \
+      (c)->trace_name[(size_t)slot_] = #kernel;                  \
+      trace_stamp_kernel<<<1, 1, 0, (c)->stream>>>((c)->trace.p + slot_); \
+    }                                                            \
   } while (0)
 
 void fs_apply(nsb_ctx *c, int mode, const double *xu, const double *xp, const double *d, double *y);
@@ -223,6 +241,15 @@ NcclApi &nccl() {
 // sum over ranks of `count` doubles, in place (dot products, norms, force integrals, S values)
 void allreduce_sum(nsb_ctx *c, double *buf, size_t count) {
   if (c->nranks == 1) return;
+  if (c->use_p2p && count <= (size_t)kP2PReduceSlot) {
+    // partial sums straight into the peers' staging, then a rank-ordered sum: two ~3 us launches, no NCCL
+    P2PArgs a = c->chan[4].args;
+    for (int k = 0; k <= a.n_peers; ++k) a.send_ptr[k] = (int64_t)k * (int64_t)count;
+    const unsigned grid = (unsigned)std::max<size_t>(1, ((size_t)a.n_peers * count + 255) / 256);
+    NSB_LAUNCH(c, p2p_push_kernel, grid, 256, a, 1, (const uint32_t *)nullptr, (int64_t)0, buf);
+    NSB_LAUNCH(c, p2p_reduce_kernel, 1, kP2PReduceSlot, a, (int)count, c->rank, c->nranks, buf);
+    return;
+  }
   NSB_NCCL(nccl().AllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->stream));
 }
 
@@ -299,7 +326,7 @@ void allgather_c(nsb_ctx *c, double *bc) {
 // ---- peer-memory exchanges: arena, IPC handles, channel descriptions (p2p.cuh) ----
 struct P2PBlob {  // what every rank publishes (all-gathered once through NCCL)
   cudaIpcMemHandle_t handle;
-  int64_t stage_off[4], stage_cap[4];
+  int64_t stage_off[kP2PChannels], stage_cap[kP2PChannels];
   int64_t recv_off[2][kP2PMaxPeers];  // channel 0/1: first entry of sender s inside my staging (-1: not a peer)
 };
 
@@ -315,15 +342,15 @@ void p2p_fill_common(nsb_ctx *c, int ch, const std::vector<int> &peers, const st
     a.peer_rank[k] = r;
     a.send_ptr[k] = send_ptr[k];
     char *base = (char *)c->peer_arena[r];
-    a.peer_stage[k] = (double *)(base + c->peer_stage_off[(size_t)r * 4 + ch]);
-    a.peer_cap[k] = c->peer_stage_cap[(size_t)r * 4 + ch];
+    a.peer_stage[k] = (double *)(base + c->peer_stage_off[(size_t)r * kP2PChannels + ch]);
+    a.peer_cap[k] = c->peer_stage_cap[(size_t)r * kP2PChannels + ch];
     a.peer_off[k] = peer_off[k];
     a.peer_flag[k] = (unsigned long long *)base + (size_t)ch * nr + c->rank;
   }
   a.send_ptr[a.n_peers] = send_ptr[a.n_peers];
   a.my_flags = (const unsigned long long *)c->arena.p + (size_t)ch * nr;
-  a.my_stage = (const double *)(c->arena.p + c->peer_stage_off[(size_t)c->rank * 4 + ch]);
-  a.my_cap = c->peer_stage_cap[(size_t)c->rank * 4 + ch];
+  a.my_stage = (const double *)(c->arena.p + c->peer_stage_off[(size_t)c->rank * kP2PChannels + ch]);
+  a.my_cap = c->peer_stage_cap[(size_t)c->rank * kP2PChannels + ch];
   a.state = c->p2p_state.p + ch;
   C.n_send = send_ptr[a.n_peers];
   C.ready = true;
@@ -378,9 +405,10 @@ void p2p_setup(nsb_ctx *c) {
     }
   // --- arena: [4 x nranks flags][staging of the 4 channels, two parities each] ---
   P2PBlob mine{};
-  const int64_t cap[4] = {(int64_t)c->n_ghost_nodes * d, (int64_t)vrecv_idx.size(), (int64_t)c->n_p, (int64_t)c->n_p};
-  int64_t off = ((int64_t)4 * nr * 8 + 255) / 256 * 256;
-  for (int ch = 0; ch < 4; ++ch) {
+  const int64_t cap[kP2PChannels] = {(int64_t)c->n_ghost_nodes * d, (int64_t)vrecv_idx.size(), (int64_t)c->n_p,
+                                     (int64_t)c->n_p, (int64_t)nr * kP2PReduceSlot};
+  int64_t off = ((int64_t)kP2PChannels * nr * 8 + 255) / 256 * 256;
+  for (int ch = 0; ch < kP2PChannels; ++ch) {
     mine.stage_off[ch] = off;
     mine.stage_cap[ch] = cap[ch];
     off += (2 * cap[ch] * 8 + 255) / 256 * 256;
@@ -390,7 +418,7 @@ void p2p_setup(nsb_ctx *c) {
   for (size_t k = 0; k < vpeers.size(); ++k) mine.recv_off[1][vpeers[k]] = vrecv_ptr[k];
   c->arena.alloc((size_t)off, &c->dev_bytes);
   c->arena.zero(c->stream);
-  c->p2p_state.alloc(4, &c->dev_bytes);
+  c->p2p_state.alloc(kP2PChannels, &c->dev_bytes);
   c->p2p_state.zero(c->stream);
   NSB_CUDA(cudaStreamSynchronize(c->stream));
   if (cudaIpcGetMemHandle(&mine.handle, c->arena.p) != cudaSuccess) {
@@ -405,13 +433,13 @@ void p2p_setup(nsb_ctx *c) {
   std::vector<P2PBlob> all((size_t)nr);
   recvb.download((char *)all.data(), c->stream);
   c->peer_arena.assign(nr, nullptr);
-  c->peer_stage_off.assign((size_t)nr * 4, 0);
-  c->peer_stage_cap.assign((size_t)nr * 4, 0);
+  c->peer_stage_off.assign((size_t)nr * kP2PChannels, 0);
+  c->peer_stage_cap.assign((size_t)nr * kP2PChannels, 0);
   int ok = 1;
   for (int r = 0; r < nr; ++r) {
-    for (int ch = 0; ch < 4; ++ch) {
-      c->peer_stage_off[(size_t)r * 4 + ch] = all[r].stage_off[ch];
-      c->peer_stage_cap[(size_t)r * 4 + ch] = all[r].stage_cap[ch];
+    for (int ch = 0; ch < kP2PChannels; ++ch) {
+      c->peer_stage_off[(size_t)r * kP2PChannels + ch] = all[r].stage_off[ch];
+      c->peer_stage_cap[(size_t)r * kP2PChannels + ch] = all[r].stage_cap[ch];
     }
     if (r == me) {
       c->peer_arena[r] = c->arena.p;
@@ -470,6 +498,9 @@ void p2p_setup(nsb_ctx *c) {
       }
     p2p_fill_common(c, 2, peers, sp, po);
     c->chan[2].n_recv = c->n_p;
+    // --- channel 4: all-reduce of a few doubles; my partial sums land in slot `me` of every peer ---
+    std::vector<int64_t> sp4(peers.size() + 1, 0), po4(peers.size(), (int64_t)me * kP2PReduceSlot);
+    p2p_fill_common(c, 4, peers, sp4, po4);
   }
   NSB_CUDA(cudaStreamSynchronize(c->stream));
   c->h_rps = {};
@@ -1129,8 +1160,15 @@ double *amg_vcycle(nsb_ctx *c, size_t l, const double *b) {
   AmgLevel &L = *c->amg[l];
   const CsrDev &M = amg_matrix(c, l);
   const double *dinv = amg_dinv(c, l);
-  if (l + 1 == c->amg.size())
+  if (l + 1 == c->amg.size()) {
+    if (M.n_rows <= kCoarseFusedMax) {
+      const unsigned threads = (unsigned)((M.n_rows + 31) / 32 * 32);
+      NSB_LAUNCH(c, coarse_cheb_kernel, 1, threads, M.view(), dinv, b, c->amg_coarse_sweeps, L.lmax, c->amg_coarse_ratio,
+                 L.z0.p);
+      return L.z0.p;
+    }
     return cheb_smooth(c, M, dinv, b, nullptr, L.z0.p, L.z1.p, L.d.p, c->amg_coarse_sweeps, L.lmax, c->amg_coarse_ratio);
+  }
   if (l == 0 && c->dist_schur) {
     // Fine level on several GPUs: every rank smooths and restricts its OWNED rows of the (replicated) matrix;
     // b is valid on the owned rows.  Aggregates do not cross ranks (coarsen(..., owner)), so the owned rows of
@@ -1518,6 +1556,11 @@ int nsb_create(int dim, int device_id, nsb_ctx **out) {
     NSB_CUDA(cudaEventCreate(&c->ev_t1));
     c->errflag.alloc(1, &c->dev_bytes);
     c->errflag.zero(c->stream);
+    if (std::getenv("NSB_TRACE")) {
+      c->trace.alloc((size_t)kTraceSlots, &c->dev_bytes);
+      c->trace.zero(c->stream);
+      c->trace_name.assign((size_t)kTraceSlots, nullptr);
+    }
   });
   if (rc != NSB_OK) {
     delete c;
@@ -1531,6 +1574,19 @@ void nsb_destroy(nsb_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->trace.p) {
+    std::vector<unsigned long long> t((size_t)kTraceSlots);
+    if (cudaMemcpy(t.data(), c->trace.p, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      const std::string path = std::string(std::getenv("NSB_TRACE")) + std::to_string(c->rank) + ".csv";
+      if (FILE *f = std::fopen(path.c_str(), "w")) {
+        std::fprintf(f, "slot,kernel,end_ns\n");
+        for (int64_t i = 0; i < kTraceSlots; ++i)
+          if (c->trace_name[(size_t)i] && t[(size_t)i])
+            std::fprintf(f, "%lld,\"%s\",%llu\n", (long long)i, c->trace_name[(size_t)i], t[(size_t)i]);
+        std::fclose(f);
+      }
+    }
+  }
   // graphs that contain NCCL kernels must go before the communicator
   if (c->prec_exec) cudaGraphExecDestroy(c->prec_exec);
   if (c->prec_graph) cudaGraphDestroy(c->prec_graph);
@@ -1862,9 +1918,9 @@ int nsb_solve_time_step(nsb_ctx *c, int *iters, double *t_prec, double *t_solve)
     halo_exchange(c, c->sol.p);           // solution = solution_owned (ghost import), reference :395
     NSB_CUDA(cudaStreamSynchronize(c->stream));
     if (c->use_p2p) {
-      P2PState st[4];
+      P2PState st[kP2PChannels];
       c->p2p_state.download(st, c->stream);
-      for (int ch = 0; ch < 4; ++ch)
+      for (int ch = 0; ch < kP2PChannels; ++ch)
         if (st[ch].error) throw NcclError("peer-memory exchange timed out on channel " + std::to_string(ch));
     }
     auto t2 = std::chrono::high_resolution_clock::now();

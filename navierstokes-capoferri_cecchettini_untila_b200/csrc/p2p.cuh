@@ -30,6 +30,8 @@
 namespace nsb {
 
 constexpr int kP2PMaxPeers = 16;
+constexpr int kP2PChannels = 5;    // see nsb_ctx
+constexpr int kP2PReduceSlot = 128;  // doubles per rank in the all-reduce staging (>= 2 * restart + 2)
 constexpr unsigned long long kP2PTimeoutNs = 5ull * 1000ull * 1000ull * 1000ull;
 
 struct P2PState {               // device memory, one per channel
@@ -83,14 +85,20 @@ __global__ void __launch_bounds__(256) p2p_push_kernel(P2PArgs a, int width, con
     const int64_t src = idx != nullptr ? (int64_t)idx[i] : base + (i - a.send_ptr[k]);
     a.peer_stage[k][par * a.peer_cap[k] + (a.peer_off[k] + (i - a.send_ptr[k])) * width + c] = x[src * width + c];
   }
-  __threadfence_system();
+  // one system-scope fence per CTA (after the barrier it covers the stores of all its threads; a fence in every
+  // thread cost ~5 us per exchange), then the last CTA to arrive releases the flags
   __syncthreads();
   __shared__ bool last;
-  if (threadIdx.x == 0) last = atomicAdd(&a.state->push_count, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = atomicAdd(&a.state->push_count, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (last) {
-    __threadfence_system();
-    if ((int)threadIdx.x < a.n_peers) st_release_sys(a.peer_flag[threadIdx.x], e);
+    if ((int)threadIdx.x < a.n_peers) {
+      __threadfence_system();
+      st_release_sys(a.peer_flag[threadIdx.x], e);
+    }
     if (threadIdx.x == 0) a.state->push_count = 0;
   }
 }
@@ -135,6 +143,36 @@ __global__ void __launch_bounds__(256) p2p_unpack_kernel(P2PArgs a, int width, c
     a.state->unpack_count = 0;
     a.state->epoch = e;
   }
+}
+
+// all-reduce of `count` <= kP2PReduceSlot doubles: every rank has pushed its partial sums into slot `my rank`
+// of all peers' staging (p2p_push_kernel, contiguous mode); sum the slots in rank order -- the same order on
+// every rank, so all ranks get bit-identical results and take the same branches -- and write buf in place.
+__global__ void __launch_bounds__(kP2PReduceSlot) p2p_reduce_kernel(P2PArgs a, int count, int my_rank, int n_ranks,
+                                                                   double *__restrict__ buf) {
+  const unsigned long long e = a.state->epoch + 1;
+  const int64_t par = (int64_t)(e & 1ull);
+  if ((int)threadIdx.x < a.n_peers) {
+    const unsigned long long *f = a.my_flags + a.peer_rank[threadIdx.x];
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) < e) {
+      if (global_ns() - t0 > kP2PTimeoutNs) {
+        a.state->error = 1;
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+  const double *st = a.my_stage + par * a.my_cap;
+  const int i = threadIdx.x;
+  if (i < count) {
+    double s = 0.0;
+    for (int r = 0; r < n_ranks; ++r) s += r == my_rank ? buf[i] : __ldcv(st + (int64_t)r * kP2PReduceSlot + i);
+    buf[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) a.state->epoch = e;
 }
 
 // Host-side description of one channel.
