@@ -28,6 +28,13 @@ const char *nsh_last_error(void);
  * "naca2412" (C4), "channel2d", "channel3d"; h = target edge length. */
 int nsh_problem_generate(const char *name, double h, nsh_problem **out);
 /* gmsh ASCII .msh 2.2 / 4.1 (reference :11-17). */
+/* The reference's airfoil pre-processing without gmsh (mesh/test.py:25-41, 155-168 + tests/2D/test_naca/run_test.sh:7-9:
+ * `./test.py naca.dat 0.4 <angle>; gmsh NACA_2408.geo -2`): a contour from a .dat file in the mesh/naca.dat layout
+ * (dat_path non-empty) or the analytic NACA 4-digit family (naca4, e.g. 2408), scaled to `chord`, turned clockwise
+ * by aoa_deg about mid-chord, placed at (cx, cy) in the box [0,Lx] x [0,Ly] (test.py: 2.2 x 1.0, centre (0.4, 0.5));
+ * boundary ids 0 bottom, 1 outlet, 2 top, 3 inlet, 4 airfoil. */
+int nsh_problem_generate_airfoil(const char *dat_path, int naca4, double chord, double aoa_deg, double Lx, double Ly,
+                                 double cx, double cy, double h, nsh_problem **out);
 int nsh_problem_read(const char *msh_path, int dim, nsh_problem **out);
 int nsh_problem_from_arrays(int dim, int64_t n_verts, const double *xyz, int64_t n_cells,
                             const uint32_t *cells, int64_t n_bfaces, const uint32_t *bfaces,

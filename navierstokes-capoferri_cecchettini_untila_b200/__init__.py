@@ -53,6 +53,7 @@ def host_lib():
         L.nsh_last_error.restype = C.c_char_p
         L.nsh_problem_generate.argtypes = [C.c_char_p, C.c_double, C.POINTER(C.c_void_p)]
         L.nsh_problem_read.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.nsh_problem_generate_airfoil.argtypes = [C.c_char_p, C.c_int] + [C.c_double] * 7 + [C.POINTER(C.c_void_p)]
         L.nsh_problem_from_arrays.argtypes = [C.c_int, C.c_int64, _c_f64p, C.c_int64, _c_u32p, C.c_int64, _c_u32p,
                                               _c_i32p, C.POINTER(C.c_void_p)]
         L.nsh_problem_write_msh.argtypes = [C.c_void_p, C.c_char_p]
@@ -102,6 +103,17 @@ class Problem:
     def generate(cls, name: str, h: float) -> "Problem":
         out = C.c_void_p()
         cls._chk(host_lib().nsh_problem_generate(name.encode(), h, C.byref(out)))
+        return cls(out)
+
+    @classmethod
+    def generate_airfoil(cls, h: float, dat_path: str = "", naca4: int = 2408, chord: float = 0.4, aoa_deg: float = 0.0,
+                         box=(2.2, 1.0), centre=(0.4, 0.5)) -> "Problem":
+        """Airfoil mesh the way the reference prepares it (mesh/test.py + run_test.sh): contour from a .dat file
+        (mesh/naca.dat layout) or the NACA 4-digit family, chord scaling, angle of attack (degrees, nose down for
+        positive angles as in test.py), defaults = test.py's box and centre."""
+        out = C.c_void_p()
+        cls._chk(host_lib().nsh_problem_generate_airfoil(dat_path.encode(), naca4, chord, aoa_deg, box[0], box[1],
+                                                         centre[0], centre[1], h, C.byref(out)))
         return cls(out)
 
     @classmethod

@@ -483,8 +483,38 @@ Mesh gen_channel2d_square(double Lx, double Ly, double ox, double oy, double s, 
   return m;
 }
 
-Mesh gen_naca2d(double Lx, double Ly, double cx, double cy, int naca4, double aoa_deg, double chord,
-                int n_around, int n_radial) {
+// Airfoil pre-processing of the reference (mesh/test.py:25-41, 155-168; tests/2D/test_naca/run_test.sh:7-9):
+// contour points with the chord on [0,1] are shifted to mid-chord (x - 0.5), scaled to `chord` and turned
+// clockwise by the angle of attack (rotate(+angle) in test.py multiplies by R(-angle)); then placed at (cx, cy).
+std::vector<std::array<double, 2>> place_airfoil(const std::vector<std::array<double, 2>> &unit, double chord,
+                                                 double aoa_deg, double cx, double cy) {
+  const double a = -aoa_deg * M_PI / 180.0;
+  std::vector<std::array<double, 2>> pts;
+  for (const auto &p : unit) {
+    const double X = (p[0] - 0.5) * chord, Y = p[1] * chord;
+    pts.push_back({cx + std::cos(a) * X - std::sin(a) * Y, cy + std::sin(a) * X + std::cos(a) * Y});
+  }
+  return pts;
+}
+
+// mesh/naca.dat / mesh/naca2412.dat layout (mesh/test.py:8-21): a name line, then "x y" pairs from the trailing
+// edge over the upper side to the leading edge and back along the lower side.
+std::vector<std::array<double, 2>> read_airfoil_dat(const std::string &path, std::string *name) {
+  std::ifstream f(path);
+  if (!f) throw std::runtime_error("read_airfoil_dat: cannot open " + path);
+  std::string line;
+  std::getline(f, line);
+  if (name) *name = line;
+  std::vector<std::array<double, 2>> pts;
+  double x, y;
+  while (f >> x >> y) pts.push_back({x, y});
+  if (pts.size() < 8) throw std::runtime_error("read_airfoil_dat: fewer than 8 contour points in " + path);
+  // a closing point that repeats the first one would give a zero-length segment
+  if (std::hypot(pts.front()[0] - pts.back()[0], pts.front()[1] - pts.back()[1]) < 1e-12) pts.pop_back();
+  return pts;
+}
+
+std::vector<std::array<double, 2>> naca4_contour(int naca4, int n_around) {
   // NACA 4-digit thickness/camber (closed trailing edge variant so that the
   // contour is a closed curve; mesh/naca2412.dat is the same family sampled
   // at 35 points with a 0.0026 blunt edge).
@@ -504,8 +534,7 @@ Mesh gen_naca2d(double Lx, double Ly, double cx, double cy, int naca4, double ao
     *dy = 2 * mc / ((1 - pc) * (1 - pc)) * (pc - x);
     return mc / ((1 - pc) * (1 - pc)) * (1 - 2 * pc + 2 * pc * x - x * x);
   };
-  // contour, counter-clockwise: lower TE -> ... wait for CCW we go upper TE -> LE -> lower TE
-  // when x decreases along the upper side the traversal is counter-clockwise.
+  // counter-clockwise: trailing edge -> upper side -> leading edge -> lower side
   const int half = std::max(8, n_around / 2);
   std::vector<std::array<double, 2>> pts;
   for (int i = 0; i < 2 * half; ++i) {
@@ -520,12 +549,21 @@ Mesh gen_naca2d(double Lx, double Ly, double cx, double cy, int naca4, double ao
       px = 1.0;
       py = 0.0;
     }
-    // chord scaling about mid-chord, rotation by -aoa (mesh/test.py:25-41 turns
-    // the foil clockwise for a positive angle of attack)
-    const double a = -aoa_deg * M_PI / 180.0;
-    const double X = (px - 0.5) * chord, Y = py * chord;
-    pts.push_back({cx + std::cos(a) * X - std::sin(a) * Y, cy + std::sin(a) * X + std::cos(a) * Y});
+    pts.push_back({px, py});
   }
+  return pts;
+}
+
+Mesh gen_naca2d(double Lx, double Ly, double cx, double cy, int naca4, double aoa_deg, double chord,
+                int n_around, int n_radial) {
+  return gen_airfoil2d(Lx, Ly, cx, cy, place_airfoil(naca4_contour(naca4, n_around), chord, aoa_deg, cx, cy), chord,
+                       n_radial);
+}
+
+// O-grid between a closed contour around (cx, cy) and the box [0,Lx] x [0,Ly]; ids: contour 4, box sides
+// 0 bottom, 1 right (outlet), 2 top, 3 left (inlet) as in mesh/NACA_2412.geo:108-113 and mesh/test.py's writer.
+Mesh gen_airfoil2d(double Lx, double Ly, double cx, double cy, const std::vector<std::array<double, 2>> &pts,
+                   double chord, int n_radial) {
   // rays from the centre (cx,cy): the contour is star-shaped with respect to
   // its mid-chord point for the cambers/thicknesses of the 4-digit family.
   struct Ray {
@@ -678,6 +716,10 @@ Mesh gen_named(const std::string &name, double h) {
   if (name == "naca2412") {  // mesh/NACA_2412.geo:2-9
     const int n_around = std::max(32, (int)std::lround(2.1 / h));
     return gen_naca2d(35.0, 20.0, 10.0, 10.0, 2412, 0.0, 1.0, n_around, 48);
+  }
+  if (name == "naca2408-run_test") {  // tests/2D/test_naca/run_test.sh:7-9 at angle 0: chord 0.4 in the 2.2 x 1.0 box
+    const int n_around = std::max(32, (int)std::lround(0.85 / h));
+    return gen_naca2d(2.2, 1.0, 0.4, 0.5, 2408, 0.0, 0.4, n_around, 48);
   }
   if (name == "channel2d") {
     const int ny = std::max(2, (int)std::lround(0.41 / h));

@@ -8,6 +8,7 @@
 // boundary facets keep id 0.
 #pragma once
 #include <cstdint>
+#include <array>
 #include <string>
 #include <vector>
 
@@ -54,6 +55,16 @@ Mesh gen_channel2d_plain(double Lx, double Ly, int nx, int ny);
 // rotated by `aoa_deg` about (cx,cy) like mesh/test.py:25-41.  O-grid.
 Mesh gen_naca2d(double Lx, double Ly, double cx, double cy, int naca4,
                 double aoa_deg, double chord, int n_around, int n_radial);
+// The reference's airfoil pre-processing (mesh/test.py:25-41, 155-168): contour points with the chord on
+// [0,1] (read_airfoil_dat: the mesh/naca.dat layout, or naca4_contour) are shifted to mid-chord, scaled to
+// `chord`, turned clockwise by the angle of attack and placed at (cx, cy); gen_airfoil2d meshes the box around
+// that closed, counter-clockwise contour (which must be star-shaped with respect to (cx, cy)).
+std::vector<std::array<double, 2>> read_airfoil_dat(const std::string &path, std::string *name = nullptr);
+std::vector<std::array<double, 2>> naca4_contour(int naca4, int n_around);
+std::vector<std::array<double, 2>> place_airfoil(const std::vector<std::array<double, 2>> &unit, double chord,
+                                                 double aoa_deg, double cx, double cy);
+Mesh gen_airfoil2d(double Lx, double Ly, double cx, double cy, const std::vector<std::array<double, 2>> &contour,
+                   double chord, int n_radial);
 // Extrudes a triangle mesh in z into nz layers of prisms, each split into 3
 // tetrahedra with the smallest-vertex-index diagonal rule (conforming).
 // 3D boundary ids as in mesh/domain3D.geo:104-108: z-planes 0, outlet 1,

@@ -2,6 +2,7 @@
 #include "../../include/nsb_host.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -90,6 +91,22 @@ int nsh_problem_generate(const char *name, double h, nsh_problem **out) {
     auto *P = new nsh_problem;
     try {
       P->p.mesh = nsb::gen_named(name, h);
+    } catch (...) {
+      delete P;
+      throw;
+    }
+    *out = P;
+  });
+}
+int nsh_problem_generate_airfoil(const char *dat_path, int naca4, double chord, double aoa_deg, double Lx, double Ly,
+                                 double cx, double cy, double h, nsh_problem **out) {
+  return guarded([&] {
+    if (!(chord > 0) || !(h > 0) || !out) throw std::runtime_error("nsh_problem_generate_airfoil: bad arguments");
+    const int n_around = std::max(32, (int)std::lround(2.1 * chord / h));
+    const auto unit = (dat_path && *dat_path) ? nsb::read_airfoil_dat(dat_path) : nsb::naca4_contour(naca4, n_around);
+    auto *P = new nsh_problem;
+    try {
+      P->p.mesh = nsb::gen_airfoil2d(Lx, Ly, cx, cy, nsb::place_airfoil(unit, chord, aoa_deg, cx, cy), chord, 48);
     } catch (...) {
       delete P;
       throw;

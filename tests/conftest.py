@@ -61,7 +61,12 @@ def make_configured_case(pkg, oracle_mod, mesh, h, uniform, um, re, dt, sin, nu=
     inlet profile, U_m, optional set_re_number(re) (evaluated at t = 0 like the drivers do), deltat and
     the sin(pi t/8) inlet factor of the *_03 drivers.  Returns (prob, orc, dim, nu)."""
     kind = pkg.INLET_UNIFORM if uniform else pkg.INLET_PARABOLIC
-    prob = pkg.Problem.generate(mesh, h).build(inlet=(kind, um, 0.41, 1 if sin else 0))
+    if mesh.startswith("airfoil:"):  # "airfoil:<naca4>:<chord>:<angle of attack>": run_test.sh / mesh/test.py pre-processing
+        _, naca4, chord, aoa = mesh.split(":")
+        prob = pkg.Problem.generate_airfoil(h, naca4=int(naca4), chord=float(chord), aoa_deg=float(aoa))
+    else:
+        prob = pkg.Problem.generate(mesh, h)
+    prob.build(inlet=(kind, um, 0.41, 1 if sin else 0))
     dim = prob.sizes()["dim"]
     orc = oracle_mod.Oracle(dim, prob.array("xyz"), prob.array("cells"), prob.array("bfaces"), prob.array("bids"),
                             quad_rule)

@@ -29,6 +29,8 @@ CONFIGS = {
     "3d-cylinder-Re100": dict(mesh="3d-cylinder", h=0.1, uniform=False, um=2.25, re=100, dt=0.01, sin=False),
     # tests/2D/test_naca/src/test_03.cpp:15,24,41,57 (uniform inflow, default nu = 1e-3, NavierStokes.hpp:254)
     "C4-naca2412": dict(mesh="naca2412", h=0.1, uniform=True, um=1.0, re=None, dt=0.01, sin=False),
+    # tests/2D/test_naca/run_test.sh:7-9: NACA 2408 contour, chord 0.4, 10 degrees angle of attack (mesh/test.py)
+    "naca2408-aoa10-run_test": dict(mesh="airfoil:2408:0.4:10", h=0.03, uniform=True, um=1.0, re=None, dt=0.01, sin=False),
     # tests/2D/test_03/src/test_03.cpp:24-25,43,59-60: inlet x sin(pi t/8); set_re_number at t = 0 gives nu = 0
     "2d-test_03-sin-inlet-nu0": dict(mesh="2d-cylinder", h=0.05, uniform=False, um=1.5, re=100, dt=0.01, sin=True),
     # tests/3D/test_03/src/test_03.cpp:15,25,43,59-60

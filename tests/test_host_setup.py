@@ -206,3 +206,63 @@ def test_product_does_not_touch_the_oracle():
         if f.endswith((".py", ".cu")):
             txt = open(os.path.join(ROOT, "tools", f), errors="ignore").read()
             assert "ns_oracle" not in txt and "from oracle" not in txt, f
+
+
+def _airfoil_contour(prob):
+    xyz = np.array(prob.array("xyz")).reshape(-1, 2)
+    bf = np.array(prob.array("bfaces")).reshape(-1, 2)
+    bid = np.array(prob.array("bids"))
+    return xyz[np.unique(bf[bid == 4])], xyz, bid
+
+
+def test_airfoil_preprocessing_matches_the_reference_script(pkg, tmp_path):
+    """mesh/test.py:25-41, 155-168 + tests/2D/test_naca/run_test.sh:7-9: contour points shifted to mid-chord,
+    scaled to the chord, turned clockwise by the angle of attack, placed at (0.4, 0.5) in the 2.2 x 1.0 box.  The
+    boundary nodes tagged 4 must be exactly those transformed points (restated here the way test.py does it)."""
+    import math
+    dat = tmp_path / "foil.dat"
+    # a small symmetric contour in the mesh/naca.dat layout: name line, TE -> upper -> LE -> lower
+    xs = 0.5 * (1 + np.cos(np.linspace(0, math.pi, 12)))
+    yt = 0.6 * (0.2969 * np.sqrt(xs) - 0.126 * xs - 0.3516 * xs**2 + 0.2843 * xs**3 - 0.1036 * xs**4)
+    pts = [(x, y) for x, y in zip(xs, yt)] + [(x, -y) for x, y in zip(xs[-2:0:-1], yt[-2:0:-1])]
+    dat.write_text("TEST FOIL\n" + "\n".join(f"{x:.6f}     {y:.6f}" for x, y in pts) + "\n")
+    chord, angle = 0.4, 7.0
+    prob = pkg.Problem.generate_airfoil(0.03, dat_path=str(dat), chord=chord, aoa_deg=angle).build(
+        inlet=(pkg.INLET_UNIFORM, 1.0, 0.41, 0))
+    foil, xyz, bid = _airfoil_contour(prob)
+    # test.py: data = (x - 0.5, y); resize(chord); rotate(angle): angle -= ...; cos(-a), sin(-a)
+    a = -angle * math.pi / 180.0
+    want = []
+    for x, y in np.loadtxt(dat, skiprows=1):
+        X, Y = (x - 0.5) * chord, y * chord
+        want.append((0.4 + math.cos(a) * X - math.sin(a) * Y, 0.5 + math.sin(a) * X + math.cos(a) * Y))
+    want = np.array(want)
+    # every contour point of the file is a boundary-4 vertex (the O-grid adds 4 corner rays)
+    d = np.abs(foil[None, :, :] - want[:, None, :]).sum(axis=2).min(axis=1)
+    assert d.max() < 1e-12 and len(foil) in (len(want), len(want) + 4)
+    assert set(np.unique(bid)) == {0, 1, 2, 3, 4}
+    assert xyz[:, 0].min() == 0.0 and abs(xyz[:, 0].max() - 2.2) < 1e-12 and abs(xyz[:, 1].max() - 1.0) < 1e-12
+    # nose down for a positive angle of attack: the leading edge (x = 0 of the file) moves up, the trailing edge down
+    le = want[np.argmin(np.loadtxt(dat, skiprows=1)[:, 0])]
+    assert le[1] > 0.5
+    # the cells are positively oriented and the space builds
+    s = prob.sizes()
+    assert s["n_cells"] > 500 and s["n_bc"] > 0 and s["n_force_faces"] == len(foil)
+
+
+def test_make_mesh_airfoil_cli(pkg, tmp_path):
+    """`make_mesh airfoil nacaDDDD|file.dat chord angle h out.msh` stands in for test.py + gmsh (run_test.sh:7-9)."""
+    import subprocess
+    subprocess.check_call(["make", "-C", ROOT, "drivers"], stdout=subprocess.DEVNULL)
+    exe = os.path.join(ROOT, "navierstokes-capoferri_cecchettini_untila_b200", "drivers", "make_mesh")
+    out = tmp_path / "domain2D.msh"
+    subprocess.check_call([exe, "airfoil", "naca2408", "0.4", "10", "0.03", str(out)], stdout=subprocess.DEVNULL)
+    prob = pkg.Problem.read_msh(str(out), 2).build(inlet=(pkg.INLET_UNIFORM, 1.0, 0.41, 0))
+    ref = pkg.Problem.generate_airfoil(0.03, naca4=2408, chord=0.4, aoa_deg=10.0).build(
+        inlet=(pkg.INLET_UNIFORM, 1.0, 0.41, 0))
+    assert prob.sizes() == ref.sizes()
+    assert np.allclose(np.array(prob.array("xyz")), np.array(ref.array("xyz")), atol=1e-12)
+    if os.path.exists("/root/reference/mesh/naca.dat"):  # the reference's own contour file, where it lies
+        subprocess.check_call([exe, "airfoil", "/root/reference/mesh/naca.dat", "0.4", "5", "0.03", str(out)],
+                              stdout=subprocess.DEVNULL)
+        assert pkg.Problem.read_msh(str(out), 2).sizes()["n_cells"] > 500
