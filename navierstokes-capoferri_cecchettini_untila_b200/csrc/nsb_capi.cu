@@ -1685,12 +1685,15 @@ int nsb_set_halo(nsb_ctx *c, int n_neighbors, const int32_t *neighbors, const in
     if (!c->have_dofs) throw ArgError("nsb_set_halo: call nsb_set_local_dofs first");
     if (n_neighbors < 0 || (n_neighbors > 0 && (!neighbors || !send_ptr || !recv_ptr)))
       throw ArgError("nsb_set_halo: null input");
-    c->neighbors.assign(neighbors, neighbors + n_neighbors);
-    c->send_ptr.assign(send_ptr, send_ptr + n_neighbors + 1);
-    c->recv_ptr.assign(recv_ptr, recv_ptr + n_neighbors + 1);
-    if (n_neighbors == 0) {
+    if (n_neighbors == 0) {  // a rank without neighbours may pass null lists
+      c->neighbors.clear();
       c->send_ptr = {0};
       c->recv_ptr = {0};
+    } else {
+      c->neighbors.assign(neighbors, neighbors + n_neighbors);
+      c->send_ptr.assign(send_ptr, send_ptr + n_neighbors + 1);
+      c->recv_ptr.assign(recv_ptr, recv_ptr + n_neighbors + 1);
+      if (c->send_ptr.back() > 0 && !send_idx) throw ArgError("nsb_set_halo: null send list");
     }
     if (c->recv_ptr.back() != (int64_t)c->n_ghost_nodes) throw ArgError("nsb_set_halo: receive counts != ghost count");
     for (int64_t i = 0; i < c->send_ptr.back(); ++i)

@@ -4,6 +4,9 @@
 // is part of the de-facto interface (forces_vs_time.csv).
 #include "NavierStokes.hpp"
 
+#include <fcntl.h>
+#include <sys/stat.h>
+
 #include <chrono>
 #include <cstdlib>
 #include <iomanip>
@@ -191,26 +194,44 @@ void NavierStokes::setup_distributed() {
   check(nsb_set_halo(ctx, (int)L.neighbors.size(), L.neighbors.data(), L.send_ptr.data(), L.send_idx.data(),
                      L.recv_ptr.data()),
         "nsb_set_halo");
+  // The 128-byte NCCL id goes from rank 0 to the others through a file.  Its name carries a per-launch nonce
+  // (the launcher's run id / rendezvous port, else the parent pid) so that a stale file of a crashed run is never
+  // read; rank 0 creates it exclusively (0600) under a temporary name and renames it into place.
   char id[128];
   const char *rdv = std::getenv("NSB_RENDEZVOUS");
-  const std::string path = rdv ? rdv : "/tmp/nsb_nccl_id_" + std::to_string((long)getppid());
+  std::string nonce;
+  for (const char *k : {"TORCHELASTIC_RUN_ID", "MASTER_PORT"})
+    if (const char *v = std::getenv(k)) nonce += std::string("_") + v;
+  const std::string path = rdv ? rdv : "/tmp/nsb_nccl_id_" + std::to_string((long)getuid()) + nonce + "_" + std::to_string((long)getppid());
   if (mpi_rank == 0) {
     if (nsb_comm_unique_id(id) != NSB_OK) throw std::runtime_error("nsb_comm_unique_id failed (libnccl.so.2?)");
     const std::string tmp = path + ".tmp";
-    FILE *f = std::fopen(tmp.c_str(), "wb");
-    if (!f || std::fwrite(id, 1, 128, f) != 128) throw std::runtime_error("cannot write " + tmp);
-    std::fclose(f);
-    std::rename(tmp.c_str(), path.c_str());
+    ::unlink(tmp.c_str());
+    ::unlink(path.c_str());  // left behind by a run that died between rename and remove
+    const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL, 0600);
+    if (fd < 0) throw std::runtime_error("cannot create " + tmp);
+    const bool ok = ::write(fd, id, 128) == 128;
+    ::close(fd);
+    if (!ok || std::rename(tmp.c_str(), path.c_str()) != 0) {
+      ::unlink(tmp.c_str());
+      throw std::runtime_error("cannot write the NCCL id to " + path);
+    }
   } else {
     bool got = false;
-    for (int tries = 0; tries < 1200 && !got; ++tries) {
-      if (FILE *f = std::fopen(path.c_str(), "rb")) {
-        got = std::fread(id, 1, 128, f) == 128;
-        std::fclose(f);
+    // only a file younger than this process can belong to this launch
+    const auto started = std::chrono::system_clock::now() - std::chrono::seconds(600);
+    for (int tries = 0; tries < 2400 && !got; ++tries) {
+      struct stat sb;
+      if (::stat(path.c_str(), &sb) == 0 && sb.st_size == 128 &&
+          std::chrono::system_clock::from_time_t(sb.st_mtime) > started) {
+        if (FILE *f = std::fopen(path.c_str(), "rb")) {
+          got = std::fread(id, 1, 128, f) == 128;
+          std::fclose(f);
+        }
       }
       if (!got) std::this_thread::sleep_for(std::chrono::milliseconds(50));
     }
-    if (!got) throw std::runtime_error("timed out waiting for the NCCL id at " + path);
+    if (!got) throw std::runtime_error("timed out (120 s) waiting for the NCCL id of rank 0 at " + path);
   }
   check(nsb_comm_init(ctx, (int)mpi_rank, (int)mpi_size, id), "nsb_comm_init");
   if (mpi_rank == 0) std::remove(path.c_str());  // every rank has joined once comm_init returns

@@ -108,8 +108,10 @@ LocalProblem localize(const Problem &P, int n_parts, int rank) {
       for (int c = 0; c < dim; ++c) rows.push_back(dim * A + c);
     L.a01 = extract_rows(P.pat.a01, rows, d.n_p, [&](uint32_t V) { return L.p_perm[V]; });
   }
-  L.a10 = extract_rows(P.pat.a10, own_pv, dim * (L.n_own + L.n_ghost),
-                       [&](uint32_t u) { return dim * local_of(u / dim) + u % dim; });
+  L.a10 = extract_rows(P.pat.a10, own_pv, dim * (L.n_own + L.n_ghost), [&](uint32_t u) {
+    const uint32_t a = local_of(u / dim);  // an unmapped node must not wrap around in dim * a + c
+    return a == UINT32_MAX ? UINT32_MAX : (uint32_t)(dim * a + u % dim);
+  });
   {
     std::vector<uint32_t> inv(d.n_pverts);
     for (uint32_t V = 0; V < d.n_pverts; ++V) inv[L.p_perm[V]] = V;
@@ -117,6 +119,9 @@ LocalProblem localize(const Problem &P, int n_parts, int rank) {
   }
   for (uint32_t v : L.fs.colind)
     if (v == UINT32_MAX) throw std::runtime_error("localize: a column of an owned row is not local");
+  for (uint32_t v : L.a10.colind)
+    if (v >= (uint32_t)dim * (L.n_own + L.n_ghost))
+      throw std::runtime_error("localize: a velocity column of an owned pressure row is not local");
   // halo lists: node B owned by r is a ghost on q iff a cell containing B also contains a node owned by q
   {
     std::vector<std::pair<int32_t, uint32_t>> send, recv;  // (peer, distributed node id)
