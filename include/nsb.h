@@ -93,11 +93,17 @@ int nsb_set_inner(nsb_ctx *ctx, int sweeps_F, double eig_ratio_F, int sweeps_S, 
  * one V-cycle over an aggregation hierarchy whose smoother is the same
  * Chebyshev-Jacobi sweep (smoother_sweeps per side, default 1 -- measured on B200 at 9.7 M DoFs:
  * 485 ms/step with 1, 514 with 2, 564 with 3;
- * strength-of-connection threshold theta, default 0.08; coarse-correction
+ * strength-of-connection threshold theta (measure and defaults: nsb_set_schur_strength); coarse-correction
  * scaling omega, default 1.5; `cycles` V-cycles per application, default 1).
  * Arguments <= 0 keep the defaults. */
 int nsb_set_schur_solver(nsb_ctx *ctx, int mode, int smoother_sweeps, double strength_theta, double omega,
                          int cycles);
+
+/* Strength-of-connection measure of the aggregation hierarchy: 0: -s_ij >= theta max_k(-s_ik) (default in 2D,
+ * theta 0.35, no decay); 1: |s_ij| >= theta sqrt(s_ii s_jj) (default in 3D, theta 0.08, decay 0.5);
+ * 2: |s_ij| >= theta max_k |s_ik|.  theta is multiplied by decay_per_level on every coarser level.
+ * measure -1 / theta 0 / decay 0 select the defaults.  Rebuilds the hierarchy at the next step. */
+int nsb_set_schur_strength(nsb_ctx *ctx, int measure, double theta, double decay_per_level);
 
 /* ---- state ------------------------------------------------------------ */
 int nsb_set_solution(nsb_ctx *ctx, const double *x_host);   /* n_u+n_p, host -> device */
@@ -156,6 +162,10 @@ int nsb_timers(const nsb_ctx *ctx, double out_ms[4]);
  *            Schur hierarchy is distributed over the ranks */
 int nsb_info(const nsb_ctx *ctx, int64_t out[20]);
 
+/* Parameters of the inner F polynomial in effect for the last step: [0] degree k, [1] lmax/lmin ratio of the real
+ * interval, [2] lambda_max(D^-1 F) estimate, [3] imaginary half-axis of the ellipse (0 for a symmetric F). */
+int nsb_inner_params(const nsb_ctx *ctx, double out[4]);
+
 /* Host-only check of the slab (windowed sliced-ELL) storage the solver kernels stream F_s from
  * (csrc/slab.cuh): builds the layout from a node-level CSR pattern and evaluates y = (F_s (x) I_dim) x
  * on the host in exactly the order the device kernels use.  No device is touched.
@@ -169,6 +179,17 @@ int nsb_slab_host_check(int dim, int64_t n_rows, int64_t n_cols, const int64_t *
 int nsb_gslab_host_check(int dim, int64_t n_nodes, int64_t n_node_cols, const int64_t *node_rowptr,
                          const uint32_t *node_colind, uint32_t window_cap, const int64_t *rowptr01,
                          const uint32_t *colind01, const double *val01, const double *xp, double *y, int64_t stats[3]);
+
+/* Host-only: coefficients of the degree-k Chebyshev-Jacobi polynomial the inner F solve of
+ * PreconditionASIMPLE::vmult (reference src/NavierStokes.cpp:978-981) is replaced by, for the ellipse with
+ * real interval [lmax/ratio, lmax] and imaginary half-axis imag (imag = 0: the interval polynomial):
+ *   z_1 = inv_theta Dinv b,   z_{i+1} = z_i + c1[i] (z_i - z_{i-1}) + c2[i] Dinv (b - F z_i),  1 <= i < k.
+ * c1, c2: k doubles each (entry 0 unused).  No device is touched. */
+int nsb_cheb_coeffs_host_check(int k, double lmax, double ratio, double imag, double *inv_theta, double *c1, double *c2);
+
+/* Host-only: largest singular value of the skew part of a dense m x m matrix (row-major) and its right singular
+ * vector y (m doubles) -- the small eigenproblem behind the estimate of the imaginary extent of D^-1 F. */
+int nsb_skew_radius_host_check(int m, const double *H, double *sigma, double *y);
 
 /* pinned host memory for callers that want asynchronous copies */
 void *nsb_alloc_pinned(int64_t bytes);

@@ -7,7 +7,7 @@
 // a single-level Chebyshev-Jacobi polynomial needs ~sqrt(cond) ~ 1/h sweeps
 // (SURVEY.md H4).  Here the same Chebyshev-Jacobi sweeps are used as the
 // smoother of a V-cycle over an aggregation hierarchy:
-//   * aggregates: greedy, strength-of-connection |s_ij| >= theta sqrt(s_ii s_jj),
+//   * aggregates: greedy on a strength-of-connection graph (see coarsen for the measures),
 //     at most `max_agg` members, built ONCE on the host from the first S;
 //   * prolongation: piecewise constant, coarse correction scaled by omega;
 //   * coarse operators: Galerkin sums S_c[I,J] = sum_{i in I, j in J} S[i,j],
@@ -108,16 +108,29 @@ struct HostCoarsening {
 // Greedy aggregation on the strength graph, visiting rows in index order; a
 // root takes its (up to max_agg-1) strongest still-free strong neighbours; a
 // row whose strong neighbours are all taken joins its strongest neighbour.
-// owner (optional, n entries, non-decreasing): aggregates never mix rows of different owners, so on
-// several GPUs every coarse row is the sum of fine rows of ONE rank and -- rows being visited in index
-// order -- every rank's aggregates get a contiguous range of coarse ids.
-inline HostCoarsening coarsen(const HostCsr &M, double theta, int max_agg, const int32_t *owner = nullptr) {
+// Strength of connection, three measures (nsb_set_schur_strength; defaults per dimension in amg_build):
+//   0 (Ruge-Stueben): j is strong for i when -s_ij >= theta * max_k(-s_ik) -- negative couplings only, relative to
+//     the row.  S = B D^-1 Bt of Taylor-Hood has a fifth of its off-diagonal entries POSITIVE (aggregating along them
+//     puts nodes together whose smooth-error values differ), and an absolute threshold does not transfer across a
+//     graded mesh: on the NACA 2408 / 10 degrees mesh of run_test.sh (cells from 0.002 to 0.03, cond(D^-1 S) = 8000 at
+//     720 rows) measure 1 at 0.08 leaves V S with eigenvalues down to 0.005 and the outer GMRES needs 750 iterations
+//     where an exact Schur solve needs 129; measure 0 at 0.35: 122 (tests/amg_emul.py; B200: 121).
+//   1: |s_ij| >= theta sqrt(s_ii s_jj), theta halved per level.  On the uniform 3D cylinder mesh at 9.7 M DoFs (B200)
+//     it needs 99 outer iterations where measure 0 needs 141 (theta 0.35) / 107 (0.2, halved per level).
+// measure 0: relative, negative couplings (above);  1: |s_ij| >= theta sqrt(s_ii s_jj) (absolute, symmetric);
+//         2: |s_ij| >= theta max_k |s_ik| (relative, either sign)
+inline HostCoarsening coarsen(const HostCsr &M, double theta, int max_agg, const int32_t *owner = nullptr,
+                              int measure = 0) {
   const int64_t n = M.n;
   HostCoarsening C;
-  std::vector<double> diag(n, 0.0);
+  std::vector<double> rowmax(n, 0.0), diag(n, 0.0);  // strongest coupling of the row (all neighbours, any owner)
   for (int64_t i = 0; i < n; ++i)
-    for (int64_t k = M.rowptr[i]; k < M.rowptr[i + 1]; ++k)
-      if (M.colind[k] == (uint32_t)i) diag[i] = std::fabs(M.val[k]);
+    for (int64_t k = M.rowptr[i]; k < M.rowptr[i + 1]; ++k) {
+      if (M.colind[k] != (uint32_t)i)
+        rowmax[i] = std::max(rowmax[i], measure == 0 ? -M.val[k] : std::fabs(M.val[k]));
+      else
+        diag[i] = std::fabs(M.val[k]);
+    }
   C.agg.assign(n, UINT32_MAX);
   uint32_t na = 0;
   std::vector<std::pair<double, uint32_t>> nb;
@@ -130,8 +143,8 @@ inline HostCoarsening coarsen(const HostCsr &M, double theta, int max_agg, const
       const uint32_t j = M.colind[k];
       if (j == (uint32_t)i) continue;
       if (owner && owner[j] != owner[i]) continue;
-      const double w = std::fabs(M.val[k]);
-      if (w < theta * std::sqrt(diag[i] * diag[j])) continue;
+      const double w = measure == 0 ? -M.val[k] : std::fabs(M.val[k]);
+      if (!(w > 0) || w < theta * (measure == 1 ? std::sqrt(diag[i] * diag[j]) : rowmax[i])) continue;
       if (C.agg[j] == UINT32_MAX)
         nb.push_back({w, j});
       else if (w > best_w) {

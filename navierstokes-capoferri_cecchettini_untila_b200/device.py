@@ -23,7 +23,7 @@ SYMBOLS = [
     "nsb_bench_kernel", "nsb_launch_count", "nsb_timers", "nsb_info", "nsb_alloc_pinned", "nsb_free_pinned",
     "nsb_comm_unique_id", "nsb_comm_init", "nsb_set_local_dofs", "nsb_set_halo", "nsb_set_schur_solver", "nsb_gather_velocity",
     "nsb_slab_host_check", "nsb_gslab_host_check", "nsb_get_lumped_mass_inv",
-    "nsb_timer_start", "nsb_timer_stop",
+    "nsb_timer_start", "nsb_timer_stop", "nsb_cheb_coeffs_host_check", "nsb_skew_radius_host_check", "nsb_inner_params", "nsb_set_schur_strength",
 ]
 
 
@@ -114,6 +114,33 @@ def slab_host_check(dim, rowptr, colind, val, x, n_cols=None, window_cap=1408):
     if rc != 0:
         raise DeviceError(f"nsb_slab_host_check failed ({rc})")
     return y, dict(zip(["slabs", "nnz", "padded", "max_window", "window_total", "bank_wavefronts_permille"], [int(v) for v in st]))
+
+
+def cheb_coeffs(k, lmax, ratio, imag=0.0):
+    """Coefficients (1/theta, c1[1:k], c2[1:k]) of the F polynomial for an ellipse (host only)."""
+    L = device_lib()
+    L.nsb_cheb_coeffs_host_check.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    it = C.c_double()
+    c1, c2 = np.zeros(k), np.zeros(k)
+    rc = L.nsb_cheb_coeffs_host_check(k, lmax, ratio, imag, C.byref(it), _p(c1, C.c_double), _p(c2, C.c_double))
+    if rc != 0:
+        raise DeviceError(f"nsb_cheb_coeffs_host_check failed ({rc})")
+    return it.value, c1, c2
+
+
+def skew_radius(H):
+    """Largest singular value of the skew part of a small dense matrix and its right singular vector (host only)."""
+    H = np.ascontiguousarray(H, np.float64)
+    m = H.shape[0]
+    L = device_lib()
+    L.nsb_skew_radius_host_check.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    sig = C.c_double()
+    y = np.zeros(m)
+    rc = L.nsb_skew_radius_host_check(m, _p(H, C.c_double), C.byref(sig), _p(y, C.c_double))
+    if rc != 0:
+        raise DeviceError(f"nsb_skew_radius_host_check failed ({rc})")
+    return sig.value, y
 
 
 def gslab_host_check(dim, node_rowptr, node_colind, rowptr01, colind01, val01, xp, window_cap=1408):
@@ -256,6 +283,10 @@ class Device:
     def set_schur_solver(self, mode=1, smoother_sweeps=0, theta=0.0, omega=0.0, cycles=0):
         self._chk(self.L.nsb_set_schur_solver(self.h, mode, smoother_sweeps, theta, omega, cycles))
 
+    def set_schur_strength(self, measure=0, theta=0.35, decay=1.0):
+        self.L.nsb_set_schur_strength.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        self._chk(self.L.nsb_set_schur_strength(self.h, measure, theta, decay))
+
     def set_dirichlet(self, dofs, values):
         dofs = np.ascontiguousarray(dofs, np.uint32)
         values = np.ascontiguousarray(values, np.float64)
@@ -342,6 +373,12 @@ class Device:
         out = np.empty(4, np.float64)
         self._chk(self.L.nsb_timers(self.h, _p(out, C.c_double)))
         return out
+
+    def inner_params(self):
+        out = np.zeros(4)
+        self.L.nsb_inner_params.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self._chk(self.L.nsb_inner_params(self.h, _p(out, C.c_double)))
+        return dict(zip(["degree_F", "ratio_F", "lambda_max_F", "imag_F"], [float(v) for v in out]))
 
     def info(self):
         out = (C.c_int64 * 20)()
