@@ -78,6 +78,8 @@ struct nsb_ctx {
   SlabDev fslab;                 // F_s in slab (windowed sliced-ELL) form: what the solver kernels stream
   GSlabDev gslab;                // A01 in the same slabs
   size_t fslab_smem = 0, fapply_smem = 0, gapply_smem = 0;  // dynamic shared memory of the slab kernels
+  size_t fslab_tma_smem = 0;     // ... of the bulk-copy variant of the sweep
+  bool sweep_tma = false;        // NSB_SWEEP_TMA=1: sweeps on F through fs_slab_sweep_tma_kernel
   uint32_t fslab_win_doubles = 0;
   DevBuf<double> chzA, chzB;     // Chebyshev iterates on F (rotating with chz_u; chd_u holds Dinv .* b)
   DevBuf<double> din;            // 1 / diag(F_s) per owned node
@@ -618,6 +620,15 @@ void g_apply(nsb_ctx *c, const double *xp, const double *w, const double *d, dou
 void fs_cheb_sweep(nsb_ctx *c, const double *bd, const double *z, const double *zold, double *znew, double c1, double c2) {
   const unsigned grid = (unsigned)c->fslab.n_slabs;
   const SlabView S = c->fslab.view();
+  if (c->sweep_tma) {
+    if (c->dim == 2)
+      NSB_LAUNCH_SMEM(c, fs_slab_sweep_tma_kernel<2>, grid, kSlabThreads, c->fslab_tma_smem, S, c->fslab_win_doubles,
+                      c->fslab.max_slab_entries, c->din.p, bd, z, zold, znew, c1, c2);
+    else
+      NSB_LAUNCH_SMEM(c, fs_slab_sweep_tma_kernel<3>, grid, kSlabThreads, c->fslab_tma_smem, S, c->fslab_win_doubles,
+                      c->fslab.max_slab_entries, c->din.p, bd, z, zold, znew, c1, c2);
+    return;
+  }
   if (c->dim == 2)
     NSB_LAUNCH_SMEM(c, fs_slab_sweep_kernel<2>, grid, kSlabThreads, c->fslab_smem, S, c->din.p, bd, z, zold, znew, c1, c2);
   else
@@ -1001,10 +1012,18 @@ void build_fslab(nsb_ctx *c) {
   prep((const void *)fs_slab_apply_kernel<2, 3>, c->fslab_smem);
   prep((const void *)fs_slab_apply_kernel<3, 0>, c->fapply_smem);
   prep((const void *)fs_slab_apply_kernel<3, 3>, c->fslab_smem);
+  c->fslab_tma_smem = kSlabTmaHeader + ((c->fslab_smem + 127) & ~(size_t)127) + (size_t)c->fslab.max_slab_entries * 10;
+  if (const char *e = std::getenv("NSB_SWEEP_TMA")) c->sweep_tma = std::atoi(e) != 0;
+  if (c->fslab_tma_smem > 227 * 1024) c->sweep_tma = false;
+  if (c->sweep_tma) {
+    prep((const void *)fs_slab_sweep_tma_kernel<2>, c->fslab_tma_smem);
+    prep((const void *)fs_slab_sweep_tma_kernel<3>, c->fslab_tma_smem);
+  }
   prep((const void *)fs_slab_sweep_kernel<2>, c->fslab_smem);
   prep((const void *)fs_slab_sweep_kernel<3>, c->fslab_smem);
   prep((const void *)g_slab_apply_kernel<2>, c->gapply_smem);
   prep((const void *)g_slab_apply_kernel<3>, c->gapply_smem);
+}
 }
 
 void finalize_setup(nsb_ctx *c) {

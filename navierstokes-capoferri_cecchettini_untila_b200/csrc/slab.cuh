@@ -70,13 +70,14 @@ struct SlabHost {
   std::vector<uint16_t> idx;
   uint32_t max_window = 0;
   int64_t nnz = 0;
+  int64_t max_slab_entries = 0;  // largest number of stored entries (incl. padding) of one slab
   double bank_wavefronts_per_step = 1.0;  // shared-memory wavefronts per half-warp load (1 = conflict-free)
   double bank_wavefronts_bound = 1.0;     // lower bound for this window order (most loaded residue per half-warp)
 };
 
 struct SlabDev {
   int n_slabs = 0;
-  int64_t n_rows = 0, nnz = 0, padded = 0;
+  int64_t n_rows = 0, nnz = 0, padded = 0, max_slab_entries = 0;
   uint32_t max_window = 0;
   DevBuf<uint32_t> slab_row, win_ptr, win_list, vpos, src;
   DevBuf<int64_t> slice_ptr;
@@ -161,6 +162,8 @@ inline SlabHost build_slabs(int64_t n_rows, int64_t n_cols, const int64_t *rp, c
   H.slice_ptr.assign((size_t)ns * kSlabSlices + 1, 0);
   for (size_t i = 0; i < slice_len.size(); ++i) H.slice_ptr[i + 1] = H.slice_ptr[i] + slice_len[i];
   const int64_t total = H.slice_ptr.back();
+  for (int64_t sl = 0; sl < ns; ++sl)
+    H.max_slab_entries = std::max(H.max_slab_entries, H.slice_ptr[(sl + 1) * kSlabSlices] - H.slice_ptr[sl * kSlabSlices]);
   H.idx.assign((size_t)total, 0);
   H.src.assign((size_t)total, kSlabPad);
   H.vpos.assign((size_t)n_rows, kVposNone | (kVposNone << 10) | (kVposNone << 20));
@@ -289,6 +292,7 @@ inline void upload_slabs(const SlabHost &H, int64_t n_rows, SlabDev &D, cudaStre
   D.nnz = H.nnz;
   D.padded = H.slice_ptr.back();
   D.max_window = H.max_window;
+  D.max_slab_entries = H.max_slab_entries;
   D.slab_row.upload(H.slab_row.data(), H.slab_row.size(), s, bytes);
   D.win_ptr.upload(H.win_ptr.data(), H.win_ptr.size(), s, bytes);
   D.win_list.upload(H.win_list.data(), H.win_list.size(), s, bytes);
@@ -318,8 +322,43 @@ __global__ void slab_repack_kernel(int64_t n, const uint32_t *__restrict__ src, 
 // batch 4 with 6 resident CTAs per SM (40 registers) is as fast as batches of 8 or 16, as 7-8
 // resident CTAs, as prefetching the first batch before the window is staged and as an asynchronous
 // (cp.async) window fill -- 0.34 ms per sweep in all cases; bank-aware entry order: 0.40 -> 0.345 ms.
-constexpr int kSlabBatch = 4;
+#ifndef NSB_SLAB_BATCH
+#define NSB_SLAB_BATCH 4
+#endif
+constexpr int kSlabBatch = NSB_SLAB_BATCH;
 constexpr int kSlabMinBlocks = 1536 / kSlabThreads;  // 1536 resident threads per SM (40 registers)
+// Software prefetch into L2 (prefetch.global.L2: no register, no scoreboard slot): while batch k is consumed the
+// lines of batch k + NSB_SLAB_PF are requested, and the first NSB_SLAB_PF batches plus the vectors of the epilogue
+// before the window is staged, so that the serial phases of a CTA (window fill -> stream -> epilogue, which add up
+// because at 6 CTAs per SM nothing else hides them) wait on L2 instead of HBM.  0 = off.  Measured on B200 at
+// 9.7 M DoFs (round 2, tools/time_kernels.py): sweep 0.316 ms without, 0.259 / 0.263 / 0.272 / 0.284 ms with a
+// distance of 1 / 2 / 4 / 8 batches (0.271 without the epilogue lines); batches of 8 or 6 entries with distance 1:
+// 0.266 / 0.262; batches of 2 with distance 2: 0.272.  Also tried: the window of the slab that will run in this
+// CTA's place one wave later (its list read here, the lines of x requested): 0.262, no gain.
+#ifndef NSB_SLAB_PF
+#define NSB_SLAB_PF 1
+#endif
+constexpr int kSlabPrefetch = NSB_SLAB_PF;
+#ifndef NSB_SLAB_PF_EPI
+#define NSB_SLAB_PF_EPI 1
+#endif
+#ifndef NSB_G_PF
+#define NSB_G_PF 1
+#endif
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// lines of entry pairs [p0, p0 + np) of a warp's slice: 4 lines of values and 1 line of indices per pair
+__device__ __forceinline__ void slab_prefetch_pairs(const double2 *vbase, const uint32_t *ibase, int p0, int np, int W2,
+                                                    int lane) {
+  for (int q = lane; q < 5 * np; q += 32) {
+    const int p = p0 + q / 5, l = q % 5;
+    if (p < W2) {
+      if (l < 4)
+        prefetch_l2(vbase + 32 * p + 8 * l);
+      else
+        prefetch_l2(ibase + 32 * p);
+    }
+  }
+}
 template <int DIM, int BATCH>
 __device__ __forceinline__ void slab_product(const SlabView &S, int s, const double *__restrict__ x, double *sm,
                                              double (&acc)[DIM]) {
@@ -331,6 +370,7 @@ __device__ __forceinline__ void slab_product(const SlabView &S, int s, const dou
   const double2 *__restrict__ v = reinterpret_cast<const double2 *>(S.val + base) + (t & 31);
   const uint32_t *__restrict__ ix = reinterpret_cast<const uint32_t *>(S.idx + base) + (t & 31);
   const uint32_t w0 = S.win_ptr[s], nw = S.win_ptr[s + 1] - w0;
+  if (kSlabPrefetch > 0) slab_prefetch_pairs(v - (t & 31), ix - (t & 31), 0, kSlabPrefetch * (BATCH / 2), W2, t & 31);
   for (uint32_t i = t; i < DIM * nw; i += kSlabThreads) {
     const uint32_t node = __ldg(S.win_list + w0 + i / DIM);
     sm[i] = __ldg(x + (size_t)DIM * node + i % DIM);
@@ -341,10 +381,111 @@ __device__ __forceinline__ void slab_product(const SlabView &S, int s, const dou
   for (int k = 0; k < W2; k += BATCH / 2) {
     double2 a[BATCH / 2];
     uint32_t j[BATCH / 2];
+    if (kSlabPrefetch > 0)
+      slab_prefetch_pairs(v - (t & 31), ix - (t & 31), k + kSlabPrefetch * (BATCH / 2), BATCH / 2, W2, t & 31);
 #pragma unroll
     for (int u = 0; u < BATCH / 2; ++u) {
       a[u] = k + u < W2 ? __ldcs(v + 32 * (k + u)) : make_double2(0.0, 0.0);
       j[u] = k + u < W2 ? __ldcs(ix + 32 * (k + u)) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < BATCH / 2; ++u)
+#pragma unroll
+      for (int c = 0; c < DIM; ++c) {
+        acc[c] += a[u].x * sm[DIM * (j[u] & 0xffffu) + c];
+        acc[c] += a[u].y * sm[DIM * (j[u] >> 16) + c];
+      }
+  }
+  __syncthreads();  // every warp is done with the window: its space now takes the partial sums
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) sm[DIM * t + c] = acc[c];
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// Bulk-copy (TMA) variant of slab_product.  The stored entries of a slab are one contiguous range of `val`
+// and of `idx`, and slice w belongs to warp w alone: lane 0 of every warp arms a warp-private mbarrier and issues
+// two cp.async.bulk copies (its slice of val and of idx, 5-9 KB) BEFORE the window is staged, so the matrix stream
+// of the CTA is in flight during the window fill and costs neither registers nor scoreboard slots; the warp then
+// waits on its barrier and takes values and indices from shared memory.
+// MEASURED NEGATIVE (B200, 9.7 M DoFs, round 2): 0.52 ms per sweep with 256-thread slabs (100 KB of shared memory,
+// 2 CTAs = 16 warps per SM), 0.48 ms with 128-thread slabs (4 CTAs per SM), against 0.316 ms for the register-staged
+// stream and 0.259 ms with the L2 prefetch above: with the whole slab staged the CTA needs ~100 KB, so only two CTAs
+// are resident and the latencies of the window gather and of the epilogue are exposed -- the kernel needs many
+// resident warps more than it needs the copy engine.  Kept behind NSB_SWEEP_TMA=1 (parity-tested) as the starting
+// point of a persistent, double-buffered version; not used by default.  Shared memory of a CTA:
+//   [0,128) mbarriers | window / partial sums (win_doubles) | val (max_slab_entries doubles) | idx (uint16)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int kSlabTmaHeader = 128;  // bytes reserved for the mbarriers
+
+template <int DIM, int BATCH>
+__device__ __forceinline__ void slab_product_tma(const SlabView &S, int s, const double *__restrict__ x,
+                                                 unsigned char *smraw, uint32_t win_doubles, int64_t max_entries,
+                                                 double (&acc)[DIM]) {
+  static_assert(BATCH % 2 == 0, "entries are fetched in pairs");
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smraw);
+  double *sm = reinterpret_cast<double *>(smraw + kSlabTmaHeader);
+  double *sval = sm + ((win_doubles + 15u) & ~15u);  // bulk copies need 16-byte aligned destinations
+  uint16_t *sidx = reinterpret_cast<uint16_t *>(sval + max_entries);
+  const int64_t base0 = S.slice_ptr[(int64_t)s * kSlabSlices];
+  const int64_t base = S.slice_ptr[(int64_t)s * kSlabSlices + warp];
+  const int n_ent = (int)(S.slice_ptr[(int64_t)s * kSlabSlices + warp + 1] - base);  // multiple of 64
+  const int W2 = n_ent >> 6;
+  const int off = (int)(base - base0);
+  if (lane == 0) {
+    mbar_init(bars + warp, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (n_ent > 0) {
+      mbar_expect_tx(bars + warp, (unsigned)n_ent * 10u);
+      bulk_g2s(sval + off, S.val + base, (unsigned)n_ent * 8u, bars + warp);
+      bulk_g2s(sidx + off, S.idx + base, (unsigned)n_ent * 2u, bars + warp);
+    }
+  }
+  const uint32_t w0 = S.win_ptr[s], nw = S.win_ptr[s + 1] - w0;
+  for (uint32_t i = t; i < DIM * nw; i += kSlabThreads) {
+    const uint32_t node = __ldg(S.win_list + w0 + i / DIM);
+    sm[i] = __ldg(x + (size_t)DIM * node + i % DIM);
+  }
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) acc[c] = 0.0;
+  __syncthreads();  // window staged; also orders lane 0's mbarrier init before the other lanes' wait
+  if (n_ent > 0) mbar_wait(bars + warp, 0);
+  const double2 *v = reinterpret_cast<const double2 *>(sval + off) + lane;
+  const uint32_t *ix = reinterpret_cast<const uint32_t *>(sidx + off) + lane;
+  for (int k = 0; k < W2; k += BATCH / 2) {
+    double2 a[BATCH / 2];
+    uint32_t j[BATCH / 2];
+#pragma unroll
+    for (int u = 0; u < BATCH / 2; ++u) {
+      a[u] = k + u < W2 ? v[32 * (k + u)] : make_double2(0.0, 0.0);
+      j[u] = k + u < W2 ? ix[32 * (k + u)] : 0u;
     }
 #pragma unroll
     for (int u = 0; u < BATCH / 2; ++u)
@@ -383,14 +524,45 @@ __global__ void __launch_bounds__(kSlabThreads, kSlabMinBlocks)
   extern __shared__ double sm[];
   const int s = blockIdx.x;
   double acc[DIM];
-  slab_product<DIM, kSlabBatch>(S, s, z, sm, acc);
   const uint32_t r0 = S.slab_row[s], nr = S.slab_row[s + 1] - r0;
+  if (kSlabPrefetch > 0 && NSB_SLAB_PF_EPI) {  // the epilogue's operands: 16 doubles per line
+    for (uint32_t i = 16 * threadIdx.x; i < DIM * nr; i += 16 * kSlabThreads) {
+      prefetch_l2(z + (int64_t)DIM * r0 + i);
+      if (zold != nullptr) prefetch_l2(zold + (int64_t)DIM * r0 + i);
+      prefetch_l2(bd + (int64_t)DIM * r0 + i);
+    }
+    if (threadIdx.x < (nr + 15) / 16) prefetch_l2(dinv_node + r0 + 16 * threadIdx.x);
+    if (threadIdx.x < (nr + 31) / 32) prefetch_l2(S.vpos + r0 + 32 * threadIdx.x);
+  }
+  slab_product<DIM, kSlabBatch>(S, s, z, sm, acc);
   for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
     const uint32_t r = r0 + i / DIM;
     const double sc = slab_row_sum<DIM>(sm, S.vpos[r], (int)(i % DIM));
     const int64_t g = (int64_t)DIM * r0 + i;
     const double zg = __ldg(z + g);
     const double zo = zold != nullptr ? zold[g] : 0.0;  // nullptr: z_0 = 0 (second sweep of a solve)
+    znew[g] = zg + c1 * (zg - zo) + c2 * (bd[g] - dinv_node[r] * sc);
+  }
+}
+
+// The same sweep with the matrix slices staged by bulk copies (slab_product_tma)
+template <int DIM>
+__global__ void __launch_bounds__(kSlabThreads)
+    fs_slab_sweep_tma_kernel(SlabView S, uint32_t win_doubles, int64_t max_entries, const double *__restrict__ dinv_node,
+                             const double *__restrict__ bd, const double *__restrict__ z, const double *__restrict__ zold,
+                             double *__restrict__ znew, double c1, double c2) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int s = blockIdx.x;
+  double acc[DIM];
+  slab_product_tma<DIM, kSlabBatch>(S, s, z, smraw, win_doubles, max_entries, acc);
+  const double *sm = reinterpret_cast<const double *>(smraw + kSlabTmaHeader);
+  const uint32_t r0 = S.slab_row[s], nr = S.slab_row[s + 1] - r0;
+  for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
+    const uint32_t r = r0 + i / DIM;
+    const double sc = slab_row_sum<DIM>(sm, S.vpos[r], (int)(i % DIM));
+    const int64_t g = (int64_t)DIM * r0 + i;
+    const double zg = __ldg(z + g);
+    const double zo = zold != nullptr ? zold[g] : 0.0;
     znew[g] = zg + c1 * (zg - zo) + c2 * (bd[g] - dinv_node[r] * sc);
   }
 }
@@ -564,9 +736,19 @@ __device__ __forceinline__ void slab_g_product(const GSlabView &G, int s, uint32
   for (int c = 0; c < DIM; ++c) acc[c] = 0.0;
   __syncthreads();
   constexpr int B = kGSlabBatch;
+  if (NSB_G_PF > 0) {  // first batches: DIM value lines (256 B per component and step) + 64 B of indices per step
+    for (int q = (t & 31); q < 2 * DIM * NSB_G_PF * B; q += 32)
+      if (q / (2 * DIM) < W) prefetch_l2(v - (t & 31) + 16 * q);
+  }
   for (int k = 0; k < W; k += B) {
     double a[B][DIM];
     unsigned j[B];
+    if (NSB_G_PF > 0) {
+      const int k1 = k + NSB_G_PF * B;
+      for (int q = (t & 31); q < 2 * DIM * B; q += 32)
+        if (k1 + q / (2 * DIM) < W) prefetch_l2(v - (t & 31) + 32 * DIM * k1 + 16 * q);
+      if ((t & 31) == 31 && k1 < W) prefetch_l2(ix - (t & 31) + 32 * k1);
+    }
 #pragma unroll
     for (int u = 0; u < B; ++u) {
       j[u] = k + u < W ? __ldcs(ix + 32 * (k + u)) : 0u;
@@ -624,6 +806,11 @@ __global__ void __launch_bounds__(kSlabThreads) g_slab_apply_kernel(SlabView S, 
   const int s = blockIdx.x;
   const uint32_t r0 = S.slab_row[s], nr = S.slab_row[s + 1] - r0;
   double *smo = sm, *smp = sm + DIM * kSlabThreads;
+  if (NSB_G_PF > 0 && w != nullptr)
+    for (uint32_t i = 16 * threadIdx.x; i < DIM * nr; i += 16 * kSlabThreads) {
+      prefetch_l2(w + (int64_t)DIM * r0 + i);
+      prefetch_l2(d + (int64_t)DIM * r0 + i);
+    }
   slab_g_product<DIM>(G, s, r0, nr, xp, smp, smo);
   for (uint32_t i = threadIdx.x; i < DIM * nr; i += kSlabThreads) {
     const int64_t g = (int64_t)DIM * r0 + i;
