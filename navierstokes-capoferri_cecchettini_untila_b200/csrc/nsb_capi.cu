@@ -1024,7 +1024,6 @@ void build_fslab(nsb_ctx *c) {
   prep((const void *)g_slab_apply_kernel<2>, c->gapply_smem);
   prep((const void *)g_slab_apply_kernel<3>, c->gapply_smem);
 }
-}
 
 void finalize_setup(nsb_ctx *c) {
   if (c->finalized) return;
