@@ -449,7 +449,8 @@ def main():
     top = max(shares, key=lambda k: shares[k][0])
     traffic = None
     try:  # measured DRAM bytes per launch of that kernel at this mesh size, when a capture exists (profiles/)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        import glob
+        tj = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]))  # newest round
         traffic = tj.get(top.split(" ")[0], {}).get(str(a.h)) if world == 1 else None
     except Exception:
         pass
@@ -466,7 +467,7 @@ def main():
             "spmv_gbs": spmv_gbs, "spmv_frac_of_hbm": spmv_gbs / hbm_peak, "spmv_ms": ms_spmv,
             "sweep_F_gbs": sweep_gbs, "sweep_F_ms": ms_sweep, "sweep_S_gbs": sweep_s_gbs, "sweep_S_ms": ms_sweep_s,
             "schur_ms": ms_schur, "sweeps_F": info2["sweeps_F"], "schur_levels": info2["schur_levels"],
-            "gram_schmidt_reorth_passes": info2["reorth_passes"],
+            "gram_schmidt_reorth_passes": info2["reorth_passes"], "inner_F_polynomial": dev.inner_params(),
             "exchanges": ("peer memory (IPC-mapped NVLink stores)" if info2["exchange_mode"] & 1 else "NCCL") if world > 1 else "none",
             "schur_fine_level_distributed": bool(info2["exchange_mode"] & 2),
             "spmv_canonical_gbs": (spmv_canonical_bytes(info) * gb / (ms_spmv_can * 1e-3)) if ms_spmv_can else None,

@@ -21,11 +21,23 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) { return __ldcs
 // independent dependent-load chains in flight (ncu: 91 % of the stall cycles of
 // the two-deep version were long-scoreboard waits, 0.28 eligible warps/scheduler).
 constexpr int kBatch = 4;
+// Requesting the batches after the first into L2 (prefetch.global.L2) as soon as the row bounds are known -- the
+// idea that pays in the slab kernels (slab.cuh) -- does NOT pay here: measured on B200 at 9.7 M DoFs, A10 product
+// 0.181 -> 0.202 ms, sweep on S 0.0785 -> 0.0834 ms (rows of 169 / 53 entries are two batches long; the extra
+// requests cost more than the one L2-latency they save).  Off.
+#ifndef NSB_CSR_PF
+#define NSB_CSR_PF 0
+#endif
+__device__ __forceinline__ void csr_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int L>
 __device__ __forceinline__ double row_dot(const CsrView &A, int64_t row, const double *__restrict__ x, int sub) {
   const int64_t b = __ldg(A.rowptr + row), e = __ldg(A.rowptr + row + 1);
   double s = 0;
+  if (NSB_CSR_PF) {
+    for (int64_t kk = b + kBatch * L + 16 * sub; kk < e; kk += 16 * L) csr_prefetch_l2(A.val + kk);
+    for (int64_t kk = b + kBatch * L + 32 * sub; kk < e; kk += 32 * L) csr_prefetch_l2(A.colind + kk);
+  }
   for (int64_t k = b + sub; k < e; k += kBatch * L) {
     double v[kBatch];
     uint32_t c[kBatch];
