@@ -988,7 +988,7 @@ void build_fslab(nsb_ctx *c) {
   std::vector<uint32_t> ci((size_t)F.nnz);
   F.rowptr.download(rp.data(), c->stream);
   F.colind.download(ci.data(), c->stream);
-  const uint32_t cap = (c->dim == 3 ? 1408u : 2112u) * (kSlabThreads > 256 ? kSlabThreads / 256 : 1);
+  const uint32_t cap = c->dim == 3 ? kSlabWindowCap<3> : kSlabWindowCap<2>;
   const SlabHost H = build_slabs(F.n_rows, c->n_uloc / c->dim, rp.data(), ci.data(), cap);
   upload_slabs(H, F.n_rows, c->fslab, c->stream, &c->dev_bytes);
   {

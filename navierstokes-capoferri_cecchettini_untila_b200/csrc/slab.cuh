@@ -326,15 +326,19 @@ __global__ void slab_repack_kernel(int64_t n, const uint32_t *__restrict__ src, 
 #define NSB_SLAB_BATCH 4
 #endif
 constexpr int kSlabBatch = NSB_SLAB_BATCH;
-constexpr int kSlabMinBlocks = 1536 / kSlabThreads;  // 1536 resident threads per SM (40 registers)
+#ifndef NSB_SLAB_MINBLOCKS
+#define NSB_SLAB_MINBLOCKS (1536 / NSB_SLAB_THREADS)
+#endif
+constexpr int kSlabMinBlocks = NSB_SLAB_MINBLOCKS;  // 1536 resident threads per SM (40 registers)
 // Software prefetch into L2 (prefetch.global.L2: no register, no scoreboard slot): while batch k is consumed the
 // lines of batch k + NSB_SLAB_PF are requested, and the first NSB_SLAB_PF batches plus the vectors of the epilogue
 // before the window is staged, so that the serial phases of a CTA (window fill -> stream -> epilogue, which add up
 // because at 6 CTAs per SM nothing else hides them) wait on L2 instead of HBM.  0 = off.  Measured on B200 at
 // 9.7 M DoFs (round 2, tools/time_kernels.py): sweep 0.316 ms without, 0.259 / 0.263 / 0.272 / 0.284 ms with a
 // distance of 1 / 2 / 4 / 8 batches (0.271 without the epilogue lines); batches of 8 or 6 entries with distance 1:
-// 0.266 / 0.262; batches of 2 with distance 2: 0.272.  Also tried: the window of the slab that will run in this
-// CTA's place one wave later (its list read here, the lines of x requested): 0.262, no gain.
+// 0.266 / 0.262; batches of 2 with distance 2: 0.272.  Also tried: the lines of x behind the window of the slab that
+// will run in this CTA's place one wave later: 0.262, no gain; 8 or 7 resident CTAs per SM (32 registers, window cap
+// 1152 / 1280 nodes) on top of the two-round-trip window fill: 0.2475 / 0.2518 against 0.2460 with 6.
 #ifndef NSB_SLAB_PF
 #define NSB_SLAB_PF 1
 #endif
@@ -342,6 +346,20 @@ constexpr int kSlabPrefetch = NSB_SLAB_PF;
 #ifndef NSB_SLAB_PF_EPI
 #define NSB_SLAB_PF_EPI 1
 #endif
+#ifndef NSB_SLAB_FILL
+#define NSB_SLAB_FILL 1
+#endif
+#ifndef NSB_SLAB_WINCAP3
+#define NSB_SLAB_WINCAP3 1408u
+#endif
+// Look-ahead (in slabs) of the metadata / window-list prefetch below: half a wave of resident CTAs (6 per SM).
+// B200, 9.7 M DoFs: sweep 0.2460 ms without, 0.2453 with a full wave (888), 0.2424 with half a wave (444).
+#ifndef NSB_SLAB_AHEAD
+#define NSB_SLAB_AHEAD (3 * 148)
+#endif
+// largest window (in nodes) a slab may have: bounds the shared memory of the kernels and the fill's unroll
+template <int DIM>
+constexpr uint32_t kSlabWindowCap = (DIM == 3 ? NSB_SLAB_WINCAP3 : 2112u) * (kSlabThreads > 256 ? kSlabThreads / 256 : 1);
 #ifndef NSB_G_PF
 #define NSB_G_PF 1
 #endif
@@ -371,6 +389,47 @@ __device__ __forceinline__ void slab_product(const SlabView &S, int s, const dou
   const uint32_t *__restrict__ ix = reinterpret_cast<const uint32_t *>(S.idx + base) + (t & 31);
   const uint32_t w0 = S.win_ptr[s], nw = S.win_ptr[s + 1] - w0;
   if (kSlabPrefetch > 0) slab_prefetch_pairs(v - (t & 31), ix - (t & 31), 0, kSlabPrefetch * (BATCH / 2), W2, t & 31);
+#if NSB_SLAB_AHEAD
+  {  // lines of the metadata and of the window list of the slab that runs NSB_SLAB_AHEAD slabs later
+    const int sf = s + NSB_SLAB_AHEAD;
+    if (sf < S.n_slabs) {
+      const uint32_t wf = S.win_ptr[sf], nwf = S.win_ptr[sf + 1] - wf;
+      if (t == 0) {
+        prefetch_l2(S.slab_row + sf + 2 * NSB_SLAB_AHEAD);
+        prefetch_l2(S.win_ptr + sf + 2 * NSB_SLAB_AHEAD);
+        prefetch_l2(S.slice_ptr + (int64_t)(sf + NSB_SLAB_AHEAD) * kSlabSlices);
+      }
+      if (32u * t < nwf) prefetch_l2(S.win_list + wf + 32 * t);
+    }
+  }
+#endif
+#if NSB_SLAB_FILL
+  // Window fill in TWO round trips for the whole CTA: every thread first loads the indices of all its window nodes
+  // (thread t owns nodes t, t + T, ...), then issues the copies of their DIM values straight into shared memory
+  // (cp.async, 8 bytes each: no registers, nothing waits until the group is complete).  The element-strided loop it
+  // replaces went through one dependent (index -> value) pair of round trips per unrolled group of four elements;
+  // the source-level stall samples of round 2 put 35 % of the warp time before the first barrier.
+  {
+    constexpr int NPT = (kSlabWindowCap<DIM> + kSlabThreads - 1) / kSlabThreads;
+    uint32_t node[NPT];
+#pragma unroll
+    for (int q = 0; q < NPT; ++q) node[q] = t + q * kSlabThreads < nw ? __ldg(S.win_list + w0 + t + q * kSlabThreads) : 0xffffffffu;
+#pragma unroll
+    for (int q = 0; q < NPT; ++q)
+      if (node[q] != 0xffffffffu) {
+        const double *src = x + (size_t)DIM * node[q];
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sm + DIM * (t + q * kSlabThreads));
+#pragma unroll
+        for (int c = 0; c < DIM; ++c)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8 * c), "l"(src + c) : "memory");
+      }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) acc[c] = 0.0;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+#else
   for (uint32_t i = t; i < DIM * nw; i += kSlabThreads) {
     const uint32_t node = __ldg(S.win_list + w0 + i / DIM);
     sm[i] = __ldg(x + (size_t)DIM * node + i % DIM);
@@ -378,6 +437,7 @@ __device__ __forceinline__ void slab_product(const SlabView &S, int s, const dou
 #pragma unroll
   for (int c = 0; c < DIM; ++c) acc[c] = 0.0;
   __syncthreads();
+#endif
   for (int k = 0; k < W2; k += BATCH / 2) {
     double2 a[BATCH / 2];
     uint32_t j[BATCH / 2];
