@@ -122,7 +122,7 @@ struct nsb_ctx {
   // channels: 0 velocity halo, 1 pressure-vertex halo of the distributed fine level of the Schur solve,
   //           2 all-gather of the owned pressure rows, 3 all-gather of the owned rows of the first coarse level,
   //           4 all-reduce of the Gram-Schmidt inner products / norms (<= kP2PReduceSlot doubles)
-  bool use_p2p = false, dist_schur = false;
+  bool use_p2p = false, dist_schur = false, p2p_fused = true;
   DevBuf<char> arena;
   std::vector<void *> peer_arena;        // per rank, IPC-mapped (nullptr for this rank)
   std::vector<int64_t> peer_stage_off;   // [rank*kP2PChannels + channel]: byte offset of the staging inside that rank's arena
@@ -255,6 +255,10 @@ void allreduce_sum(nsb_ctx *c, double *buf, size_t count) {
   if (c->use_p2p && count <= (size_t)kP2PReduceSlot) {
     // partial sums straight into the peers' staging, then a rank-ordered sum: two ~3 us launches, no NCCL
     P2PArgs a = c->chan[4].args;
+    if (c->p2p_fused) {
+      NSB_LAUNCH(c, p2p_allreduce_kernel, 1, kP2PReduceSlot, a, (int)count, c->rank, c->nranks, buf);
+      return;
+    }
     for (int k = 0; k <= a.n_peers; ++k) a.send_ptr[k] = (int64_t)k * (int64_t)count;
     const unsigned grid = (unsigned)std::max<size_t>(1, ((size_t)a.n_peers * count + 255) / 256);
     NSB_LAUNCH(c, p2p_push_kernel, grid, 256, a, 1, (const uint32_t *)nullptr, (int64_t)0, buf);
@@ -281,14 +285,28 @@ void p2p_unpack(nsb_ctx *c, int ch, int width, int64_t recv_base, int64_t n_entr
   NSB_LAUNCH(c, p2p_unpack_kernel, grid, 256, C.args, width, C.recv_idx, recv_base, n_entries, skip_begin, skip_end, y);
 }
 
+// one exchange on channel ch: x -> peers' staging, staging -> y (one launch; NSB_P2P_FUSED=0: two)
+void p2p_exchange(nsb_ctx *c, int ch, int width, int64_t send_base, const double *x, int64_t recv_base, int64_t n_entries,
+                  int64_t skip_begin, int64_t skip_end, double *y) {
+  if (!c->p2p_fused) {
+    p2p_push(c, ch, width, send_base, x);
+    p2p_unpack(c, ch, width, recv_base, n_entries, skip_begin, skip_end, y);
+    return;
+  }
+  P2PChannel &C = c->chan[ch];
+  const int64_t total = std::max(C.n_send, n_entries) * width;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 2 * kNumSM));
+  NSB_LAUNCH(c, p2p_exchange_kernel, grid, 256, C.args, width, C.send_idx, send_base, x, C.recv_idx, recv_base, n_entries,
+             skip_begin, skip_end, y);
+}
+
 // Refresh the velocity ghosts of x from their owners (Epetra Import of the
 // reference's vmult; `solution = solution_owned`, reference :395).
 void halo_exchange(nsb_ctx *c, double *x) {
   if (c->nranks == 1 || c->neighbors.empty()) return;
   const int d = c->dim;
   if (c->use_p2p) {
-    p2p_push(c, 0, d, 0, x);
-    p2p_unpack(c, 0, d, (int64_t)c->n_own_nodes, (int64_t)c->n_ghost_nodes, 0, 0, x);
+    p2p_exchange(c, 0, d, 0, x, (int64_t)c->n_own_nodes, (int64_t)c->n_ghost_nodes, 0, 0, x);
     return;
   }
   const int64_t ns = c->send_ptr.back();
@@ -309,8 +327,7 @@ void halo_exchange(nsb_ctx *c, double *x) {
 void allgather_p(nsb_ctx *c, double *yp) {
   if (c->nranks == 1) return;
   if (c->use_p2p) {
-    p2p_push(c, 2, 1, (int64_t)c->p_begin, yp);
-    p2p_unpack(c, 2, 1, 0, (int64_t)c->n_p, (int64_t)c->p_begin, (int64_t)c->p_begin + c->n_p_own, yp);
+    p2p_exchange(c, 2, 1, (int64_t)c->p_begin, yp, 0, (int64_t)c->n_p, (int64_t)c->p_begin, (int64_t)c->p_begin + c->n_p_own, yp);
     return;
   }
   NSB_NCCL(nccl().GroupStart());
@@ -324,14 +341,12 @@ void allgather_p(nsb_ctx *c, double *yp) {
 // distributed fine level of the Schur solve: refresh the ghost vertices of a pressure-like vector
 void halo_p(nsb_ctx *c, double *z) {
   if (!c->chan[1].args.n_peers) return;
-  p2p_push(c, 1, 1, 0, z);
-  p2p_unpack(c, 1, 1, 0, c->chan[1].n_recv, 0, 0, z);
+  p2p_exchange(c, 1, 1, 0, z, 0, c->chan[1].n_recv, 0, 0, z);
 }
 // replicate the first coarse level's right-hand side from the ranks that own its rows
 void allgather_c(nsb_ctx *c, double *bc) {
   const int64_t b = c->c_offsets[c->rank], e = c->c_offsets[c->rank + 1];
-  p2p_push(c, 3, 1, b, bc);
-  p2p_unpack(c, 3, 1, 0, (int64_t)c->c_offsets[c->nranks], b, e, bc);
+  p2p_exchange(c, 3, 1, b, bc, 0, (int64_t)c->c_offsets[c->nranks], b, e, bc);
 }
 
 // ---- peer-memory exchanges: arena, IPC handles, channel descriptions (p2p.cuh) ----
@@ -371,6 +386,7 @@ void p2p_setup(nsb_ctx *c) {
   c->use_p2p = false;
   c->dist_schur = false;
   if (c->nranks == 1) return;
+  if (const char *ef = std::getenv("NSB_P2P_FUSED")) c->p2p_fused = std::atoi(ef) != 0;
   const char *env = std::getenv("NSB_P2P");
   if ((env && std::atoi(env) == 0) || c->nranks > kP2PMaxPeers) return;
   const int nr = c->nranks, me = c->rank, d = c->dim;

@@ -145,6 +145,76 @@ __global__ void __launch_bounds__(256) p2p_unpack_kernel(P2PArgs a, int width, c
   }
 }
 
+// push and unpack of one exchange in ONE launch (every launch costs 2-3 us inside the captured graph and the
+// iteration at 8 GPUs holds 12 exchanges): every CTA first stores its share of the send list into the peers'
+// staging, the last CTA to finish releases the flags, then every CTA waits for the peers' flags and copies its
+// share of the staging into the ghost slots.  A CTA never waits for CTAs of its own grid (only the flag release
+// depends on all of them, and nobody of this grid waits for it), so the grid need not be co-resident.
+__global__ void __launch_bounds__(256) p2p_exchange_kernel(P2PArgs a, int width, const uint32_t *__restrict__ send_idx,
+                                                           int64_t send_base, const double *x,
+                                                           const uint32_t *__restrict__ recv_idx, int64_t recv_base,
+                                                           int64_t n_entries, int64_t skip_begin, int64_t skip_end,
+                                                           double *y) {  // y may be x (owned entries read, ghost slots written)
+  const unsigned long long e = a.state->epoch + 1;
+  const int64_t par = (int64_t)(e & 1ull);
+  __shared__ bool last;
+  {
+    const int64_t total = a.send_ptr[a.n_peers] * width;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t i = t / width;
+      const int c = (int)(t - i * width);
+      int k = 0;
+      while (k + 1 < a.n_peers && i >= a.send_ptr[k + 1]) ++k;
+      const int64_t src = send_idx != nullptr ? (int64_t)send_idx[i] : send_base + (i - a.send_ptr[k]);
+      a.peer_stage[k][par * a.peer_cap[k] + (a.peer_off[k] + (i - a.send_ptr[k])) * width + c] = x[src * width + c];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      last = atomicAdd(&a.state->push_count, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+      if ((int)threadIdx.x < a.n_peers) {
+        __threadfence_system();
+        st_release_sys(a.peer_flag[threadIdx.x], e);
+      }
+      if (threadIdx.x == 0) a.state->push_count = 0;
+    }
+  }
+  if ((int)threadIdx.x < a.n_peers) {
+    const unsigned long long *f = a.my_flags + a.peer_rank[threadIdx.x];
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) < e) {
+      if (global_ns() - t0 > kP2PTimeoutNs) {
+        a.state->error = 1;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  const double *st = a.my_stage + par * a.my_cap;
+  const int64_t total = n_entries * width;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = t / width;
+    if (j >= skip_begin && j < skip_end) continue;
+    const int c = (int)(t - j * width);
+    const int64_t dst = recv_idx != nullptr ? (int64_t)recv_idx[j] : recv_base + j;
+    y[dst * width + c] = __ldcv(st + t);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(&a.state->unpack_count, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    a.state->unpack_count = 0;
+    a.state->epoch = e;
+  }
+}
+
 // all-reduce of `count` <= kP2PReduceSlot doubles: every rank has pushed its partial sums into slot `my rank`
 // of all peers' staging (p2p_push_kernel, contiguous mode); sum the slots in rank order -- the same order on
 // every rank, so all ranks get bit-identical results and take the same branches -- and write buf in place.
@@ -153,6 +223,43 @@ __global__ void __launch_bounds__(kP2PReduceSlot) p2p_reduce_kernel(P2PArgs a, i
   const unsigned long long e = a.state->epoch + 1;
   const int64_t par = (int64_t)(e & 1ull);
   if ((int)threadIdx.x < a.n_peers) {
+    const unsigned long long *f = a.my_flags + a.peer_rank[threadIdx.x];
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) < e) {
+      if (global_ns() - t0 > kP2PTimeoutNs) {
+        a.state->error = 1;
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+  const double *st = a.my_stage + par * a.my_cap;
+  const int i = threadIdx.x;
+  if (i < count) {
+    double s = 0.0;
+    for (int r = 0; r < n_ranks; ++r) s += r == my_rank ? buf[i] : __ldcv(st + (int64_t)r * kP2PReduceSlot + i);
+    buf[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) a.state->epoch = e;
+}
+
+// the same all-reduce in one launch: push the partial sums into slot `my rank` of every peer, release, wait, sum
+__global__ void __launch_bounds__(kP2PReduceSlot) p2p_allreduce_kernel(P2PArgs a, int count, int my_rank, int n_ranks,
+                                                                      double *__restrict__ buf) {
+  const unsigned long long e = a.state->epoch + 1;
+  const int64_t par = (int64_t)(e & 1ull);
+  for (int t = threadIdx.x; t < a.n_peers * count; t += blockDim.x) {
+    const int k = t / count, i = t - k * count;
+    a.peer_stage[k][par * a.peer_cap[k] + a.peer_off[k] + i] = buf[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < a.n_peers) {
+    __threadfence_system();
+    st_release_sys(a.peer_flag[threadIdx.x], e);
     const unsigned long long *f = a.my_flags + a.peer_rank[threadIdx.x];
     const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(f) < e) {

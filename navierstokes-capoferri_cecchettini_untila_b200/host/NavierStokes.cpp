@@ -339,7 +339,10 @@ void NavierStokes::compute_forces(const double & /*time*/) {
 void NavierStokes::solve(unsigned int time_step) {
   const bool pcout = mpi_rank == 0;
   if (pcout) std::cout << "===================================================" << std::endl;
-  std::ofstream output_file("forces_vs_time.csv");
+  // The reference lets EVERY rank write ./forces_vs_time.csv (:446); the wall-clock columns differ between ranks,
+  // so under mpirun the ranks overwrite each other's lines with text of different length.  Here rank 0 writes
+  // the file and the other ranks write the same lines to a null stream.
+  std::ofstream output_file(mpi_rank == 0 ? "forces_vs_time.csv" : "/dev/null");
   output_file << "time,deltat,GMRES_iters,time_prec_init,time_sol,Drag,Lift,Cd,Cl\n";
   if (0 == time_step) {
     time = 0.0;

@@ -294,6 +294,10 @@ if os.environ.get("STUDY") == "schur":
         print(kw, "levels", vc.sizes(), f"operator complexity {cx:.2f}", "outer its", gmres_left(asimple(Fsolve, vc.solve)), flush=True)
     sys.exit(0)
 cases = [("exact", {})]
+if os.environ.get("STUDY") == "accurate":
+    for k, ratio in ((16, 100.0), (24, 100.0), (24, 200.0), (40, 200.0)):
+        cases.append(("poly", {"k": k, "ratio": ratio, "imag": 0.4}))
+    cases.append(("gpoly", {"k": 20, "roots": None}))
 for k in (4, 6, 8, 10):
     for imag in (0.0, 0.4):
         cases.append(("poly", {"k": k, "ratio": max(6.0, (k / 1.1) ** 2), "imag": imag}))
@@ -302,6 +306,8 @@ for pre, post, ratio in ((1, 2, 10.0), (2, 2, 10.0), (3, 3, 12.0)):
 for k in (3, 4, 5, 6, 8, 10):
     cases.append(("gpoly", {"k": k, "roots": gmres_poly_roots(k)}))
 for kind, kw in cases:
+    if kind == "gpoly" and kw.get("roots") is None:
+        kw["roots"] = gmres_poly_roots(kw["k"])
     passes[0] = 0
     t0 = time.time()
     its = gmres_left(asimple(make_F(kind, **kw)))
