@@ -135,6 +135,12 @@ struct nsb_ctx {
   DevBuf<double> a10t;  // A10^T values on the pattern of A01
   // ---- Schur solve: 0 = single-level Chebyshev polynomial, 1 = multilevel V-cycle (amg.cuh) ----
   int schur_mode = 1, amg_nu = 1, amg_max_agg = 8, amg_cycles = 1, amg_coarse_sweeps = 16;
+  // Coarsening stops at amg_coarsest_rows (0 = automatic).  Levels of <= kCoarseFusedMax rows are solved by ONE
+  // single-CTA kernel, while every level above them costs ~5 launches of 3-6 us each: for large Schur blocks
+  // (> 16384 rows) the recursion therefore ends at the first level that fits that kernel (with 24 sweeps for a
+  // ratio of 150 instead of 16 for 60), small problems keep coarsening to 64 rows.  B200, 9.7 M DoFs: 7 -> 6
+  // levels, 99 -> 95-98 outer iterations, solve 372 -> 357-369 ms per step.
+  int amg_coarsest_rows = 0;
   // strength of connection of the aggregation (amg.cuh: coarsen); < 0 / 0: the default of the dimension, chosen in
   // amg_build -- 2D: relative negative couplings, theta 0.35 (graded airfoil meshes need it: 750 -> 120 outer
   // iterations on NACA 2408 at 10 degrees); 3D: |s_ij| >= 0.08 sqrt(s_ii s_jj), halved per level (9.7 M DoFs,
@@ -143,7 +149,7 @@ struct nsb_ctx {
   double amg_theta_decay = 0.0;
   double amg_theta = 0.0, amg_omega = 1.5, amg_smooth_ratio = 4.0, amg_coarse_ratio = 60.0;
   std::vector<std::unique_ptr<AmgLevel>> amg;
-  bool amg_built = false;
+  bool amg_built = false, amg_coarse_auto_strong = false;
 };
 
 namespace {
@@ -1090,6 +1096,9 @@ void finalize_setup(nsb_ctx *c) {
   dz(c->tmpN, N);
   dz(c->pz, N);
   if (const char *e = std::getenv("NSB_GRAPH")) c->use_graph = std::atoi(e) != 0;
+  if (const char *e = std::getenv("NSB_AMG_COARSEST")) c->amg_coarsest_rows = std::max(1, std::atoi(e));
+  if (const char *e = std::getenv("NSB_AMG_CSWEEPS")) c->amg_coarse_sweeps = std::max(1, std::atoi(e));
+  if (const char *e = std::getenv("NSB_AMG_CRATIO")) c->amg_coarse_ratio = std::max(2.0, std::atof(e));
   if (const char *e = std::getenv("NSB_SKEW")) c->use_skew = std::atoi(e) != 0;  // 0: interval polynomial (A/B experiments)
   dz(c->hdev, 2 * kMaxDots + 8);
   dz(c->partials, (size_t)kMaxDots * kRedBlocks);
@@ -1242,7 +1251,10 @@ void amg_build(nsb_ctx *c) {
   const int measure = c->amg_measure >= 0 ? c->amg_measure : (c->dim == 2 ? 0 : 1);
   const double theta0 = c->amg_theta > 0 ? c->amg_theta : (measure == 1 ? 0.08 : 0.35);
   const double decay = c->amg_theta_decay > 0 ? c->amg_theta_decay : (measure == 1 ? 0.5 : 1.0);
-  while (M.n > 64 && c->amg.size() < 16) {
+  const bool big = c->s.n_rows > 16384;
+  const int64_t coarsest = c->amg_coarsest_rows > 0 ? c->amg_coarsest_rows : (big ? kCoarseFusedMax : 64);
+  c->amg_coarse_auto_strong = c->amg_coarsest_rows <= 0 && big;
+  while (M.n > coarsest && c->amg.size() < 16) {
     const bool fine = c->amg.size() == 1;
     HostCoarsening C = coarsen(M, theta0 * std::pow(decay, (double)(c->amg.size() - 1)), c->amg_max_agg,
                                fine && want_dist ? owner.data() : nullptr, measure);
@@ -1327,8 +1339,9 @@ double *amg_vcycle(nsb_ctx *c, size_t l, const double *b) {
   if (l + 1 == c->amg.size()) {
     if (M.n_rows <= kCoarseFusedMax) {
       const unsigned threads = (unsigned)((M.n_rows + 31) / 32 * 32);
-      NSB_LAUNCH(c, coarse_cheb_kernel, 1, threads, M.view(), dinv, b, c->amg_coarse_sweeps, L.lmax, c->amg_coarse_ratio,
-                 L.z0.p);
+      const bool strong = c->amg_coarse_auto_strong && M.n_rows > 64;
+      NSB_LAUNCH(c, coarse_cheb_kernel, 1, threads, M.view(), dinv, b, strong ? std::max(24, c->amg_coarse_sweeps) : c->amg_coarse_sweeps,
+                 L.lmax, strong ? std::max(150.0, c->amg_coarse_ratio) : c->amg_coarse_ratio, L.z0.p);
       return L.z0.p;
     }
     return cheb_smooth(c, M, dinv, b, nullptr, L.z0.p, L.z1.p, L.d.p, c->amg_coarse_sweeps, L.lmax, c->amg_coarse_ratio);
