@@ -18,7 +18,7 @@ else:
     it, _, _ = dev.solve_time_step()
 out = {"its": it}
 for name, which in (("sweep_F", 4), ("block_spmv", 5), ("prec_apply", 2), ("g_apply", 7), ("a10_spmv", 8), ("sweep_S", 6),
-                    ("canonical_spmv", 0)):
+                    ("gram_schmidt_k14", 13), ("canonical_spmv", 0)):
     if names is not None and name not in names:
         continue
     try:
