@@ -191,6 +191,14 @@ int nsb_cheb_coeffs_host_check(int k, double lmax, double ratio, double imag, do
  * vector y (m doubles) -- the small eigenproblem behind the estimate of the imaginary extent of D^-1 F. */
 int nsb_skew_radius_host_check(int m, const double *H, double *sigma, double *y);
 
+/* Host-only: the greedy aggregation of the Schur hierarchy (csrc/amg.cuh: coarsen) on a CSR matrix.
+ * measure / theta as in nsb_set_schur_strength; owner: optional (n entries, non-decreasing) -- aggregates never mix
+ * owners.  agg_out: n entries, fine row -> aggregate; *n_coarse_out: number of aggregates; coarse_nnz_out: entries
+ * of the Galerkin pattern.  No device is touched. */
+int nsb_amg_coarsen_host_check(int64_t n, const int64_t *rowptr, const uint32_t *colind, const double *val, double theta,
+                               int max_agg, int measure, const int32_t *owner, uint32_t *agg_out, int64_t *n_coarse_out,
+                               int64_t *coarse_nnz_out);
+
 /* pinned host memory for callers that want asynchronous copies */
 void *nsb_alloc_pinned(int64_t bytes);
 void nsb_free_pinned(void *p);

@@ -2430,6 +2430,33 @@ int nsb_skew_radius_host_check(int m, const double *H, double *sigma, double *y)
   return NSB_OK;
 }
 
+int nsb_amg_coarsen_host_check(int64_t n, const int64_t *rowptr, const uint32_t *colind, const double *val, double theta,
+                               int max_agg, int measure, const int32_t *owner, uint32_t *agg_out, int64_t *n_coarse_out,
+                               int64_t *coarse_nnz_out) {
+  if (n < 1 || !rowptr || !colind || !val || !(theta > 0) || max_agg < 1 || measure < 0 || measure > 2 || !agg_out ||
+      !n_coarse_out || !coarse_nnz_out)
+    return NSB_EARG;
+  try {
+    HostCsr M;
+    M.n = n;
+    M.rowptr.assign(rowptr, rowptr + n + 1);
+    M.colind.assign(colind, colind + rowptr[n]);
+    M.val.assign(val, val + rowptr[n]);
+    const HostCoarsening C = coarsen(M, theta, max_agg, owner, measure);
+    std::copy(C.agg.begin(), C.agg.end(), agg_out);
+    *n_coarse_out = C.coarse.n;
+    *coarse_nnz_out = (int64_t)C.coarse.colind.size();
+    // Galerkin consistency: the coarse values accumulated through `pos` must equal P^T M P row sums
+    double fine = 0, coarse = 0;
+    for (double v : M.val) fine += v;
+    for (double v : C.coarse.val) coarse += v;
+    if (std::fabs(fine - coarse) > 1e-9 * (1.0 + std::fabs(fine))) return NSB_ESTRUCT;
+    return NSB_OK;
+  } catch (...) {
+    return NSB_EARG;
+  }
+}
+
 void *nsb_alloc_pinned(int64_t bytes) {
   void *p = nullptr;
   if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) {

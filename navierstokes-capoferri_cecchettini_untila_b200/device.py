@@ -23,7 +23,7 @@ SYMBOLS = [
     "nsb_bench_kernel", "nsb_launch_count", "nsb_timers", "nsb_info", "nsb_alloc_pinned", "nsb_free_pinned",
     "nsb_comm_unique_id", "nsb_comm_init", "nsb_set_local_dofs", "nsb_set_halo", "nsb_set_schur_solver", "nsb_gather_velocity",
     "nsb_slab_host_check", "nsb_gslab_host_check", "nsb_get_lumped_mass_inv",
-    "nsb_timer_start", "nsb_timer_stop", "nsb_cheb_coeffs_host_check", "nsb_skew_radius_host_check", "nsb_inner_params", "nsb_set_schur_strength",
+    "nsb_timer_start", "nsb_timer_stop", "nsb_cheb_coeffs_host_check", "nsb_skew_radius_host_check", "nsb_inner_params", "nsb_set_schur_strength", "nsb_amg_coarsen_host_check",
 ]
 
 
@@ -141,6 +141,27 @@ def skew_radius(H):
     if rc != 0:
         raise DeviceError(f"nsb_skew_radius_host_check failed ({rc})")
     return sig.value, y
+
+
+def amg_coarsen(rowptr, colind, val, theta, max_agg=8, measure=0, owner=None):
+    """Aggregates of csrc/amg.cuh: coarsen on a CSR matrix (host only).  Returns (agg, n_coarse, coarse_nnz)."""
+    rowptr = np.ascontiguousarray(rowptr, np.int64)
+    colind = np.ascontiguousarray(colind, np.uint32)
+    val = np.ascontiguousarray(val, np.float64)
+    n = rowptr.size - 1
+    L = device_lib()
+    L.nsb_amg_coarsen_host_check.argtypes = [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_uint32), C.POINTER(C.c_double),
+                                             C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint32),
+                                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    agg = np.zeros(n, np.uint32)
+    nc, nnzc = C.c_int64(), C.c_int64()
+    ow = None if owner is None else np.ascontiguousarray(owner, np.int32)
+    rc = L.nsb_amg_coarsen_host_check(n, _p(rowptr, C.c_int64), _p(colind, C.c_uint32), _p(val, C.c_double), theta, max_agg,
+                                      measure, None if ow is None else _p(ow, C.c_int32), _p(agg, C.c_uint32),
+                                      C.byref(nc), C.byref(nnzc))
+    if rc != 0:
+        raise DeviceError(f"nsb_amg_coarsen_host_check failed ({rc})")
+    return agg, nc.value, nnzc.value
 
 
 def gslab_host_check(dim, node_rowptr, node_colind, rowptr01, colind01, val01, xp, window_cap=1408):
