@@ -318,10 +318,10 @@ __global__ void slab_repack_kernel(int64_t n, const uint32_t *__restrict__ src, 
 
 // Stage the window of slab s in shared memory and form this thread's partial row sum.
 // Entries are taken kSlabBatch at a time: all (value, index) loads of a batch are issued before the
-// first use.  Measured on B200 at 9.7 M DoFs (tools/sweep_variants.py, gpurun_out/variants*.log):
-// batch 4 with 6 resident CTAs per SM (40 registers) is as fast as batches of 8 or 16, as 7-8
-// resident CTAs, as prefetching the first batch before the window is staged and as an asynchronous
-// (cp.async) window fill -- 0.34 ms per sweep in all cases; bank-aware entry order: 0.40 -> 0.345 ms.
+// first use.  Measured on B200 at 9.7 M DoFs (round 1, variant builds of this file): batch 4 with 6 resident
+// CTAs per SM (40 registers) is as fast as batches of 8 or 16 and as 7-8 resident CTAs -- 0.34 ms per sweep in all
+// cases; bank-aware entry order: 0.40 -> 0.345 ms.  The -DNSB_SLAB_* macros below are the switches of those A/B
+// builds (tools/time_kernels.py with NSB_LIBNSB=<variant>); their defaults are the measured best.
 #ifndef NSB_SLAB_BATCH
 #define NSB_SLAB_BATCH 4
 #endif
@@ -343,13 +343,13 @@ constexpr int kSlabMinBlocks = NSB_SLAB_MINBLOCKS;  // 1536 resident threads per
 #define NSB_SLAB_PF 1
 #endif
 constexpr int kSlabPrefetch = NSB_SLAB_PF;
-#ifndef NSB_SLAB_PF_EPI
+#ifndef NSB_SLAB_PF_EPI  // also request the epilogue's operands (0.271 -> 0.259 ms)
 #define NSB_SLAB_PF_EPI 1
 #endif
-#ifndef NSB_SLAB_FILL
+#ifndef NSB_SLAB_FILL  // 1: window fill in two round trips (indices, then cp.async copies); 0: element-strided loop
 #define NSB_SLAB_FILL 1
 #endif
-#ifndef NSB_SLAB_WINCAP3
+#ifndef NSB_SLAB_WINCAP3  // window capacity of a 3D slab in nodes (24 B each in shared memory)
 #define NSB_SLAB_WINCAP3 1408u
 #endif
 // Look-ahead (in slabs) of the metadata / window-list prefetch below: half a wave of resident CTAs (6 per SM).
@@ -360,7 +360,7 @@ constexpr int kSlabPrefetch = NSB_SLAB_PF;
 // largest window (in nodes) a slab may have: bounds the shared memory of the kernels and the fill's unroll
 template <int DIM>
 constexpr uint32_t kSlabWindowCap = (DIM == 3 ? NSB_SLAB_WINCAP3 : 2112u) * (kSlabThreads > 256 ? kSlabThreads / 256 : 1);
-#ifndef NSB_G_PF
+#ifndef NSB_G_PF  // prefetch distance (batches) of the A01 slabs: g_slab_apply 0.227 -> 0.194 ms with 1, same with 2
 #define NSB_G_PF 1
 #endif
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
