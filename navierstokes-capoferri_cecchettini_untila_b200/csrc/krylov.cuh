@@ -58,7 +58,9 @@ __device__ __forceinline__ int64_t active_index(int64_t e, int64_t n1, int64_t g
 // partials: (K+1) * gridDim.x doubles; counter: one unsigned, zero on entry, reset on exit.
 // Reductions are deterministic: block partials are summed in a fixed order by the last block.
 // (Requesting the next trip's lines with prefetch.global.L2, which pays in the slab kernels, costs here: both
-// passes against 14 vectors 0.453 -> 0.563 ms on B200 -- K + 1 requests per element are too many.)
+// passes against 14 vectors 0.453 -> 0.563 ms on B200 -- K + 1 requests per element are too many.  Splitting the
+// projection's chain of K dependent DFMAs into four partial sums with the coefficients in registers (the
+// source-level samples show 25 % fixed-latency stalls there) costs 26 more registers and is slower too: 0.490 ms.)
 template <int K, int U, int MODE>
 __global__ void __launch_bounds__(kRedThreads)
     ortho_kernel(const double *__restrict__ V, int64_t ld, int k, const double *__restrict__ coef, double sign,
