@@ -266,3 +266,52 @@ def test_make_mesh_airfoil_cli(pkg, tmp_path):
         subprocess.check_call([exe, "airfoil", "/root/reference/mesh/naca.dat", "0.4", "5", "0.03", str(out)],
                               stdout=subprocess.DEVNULL)
         assert pkg.Problem.read_msh(str(out), 2).sizes()["n_cells"] > 500
+
+
+def test_msh_v22_file_as_gmsh_writes_it(pkg, tmp_path):
+    """Format 2.2 in the layout gmsh itself produces (`gmsh -2 -format msh22`, what deal.II's GridIn::read_msh of
+    the reference reads, src/NavierStokes.cpp:9-17): $PhysicalNames, 15-node (point) elements that must be skipped,
+    line elements with two tags (physical, elementary), node numbers that do not start at the first used node, and
+    a clockwise triangle."""
+    txt = """$MeshFormat
+2.2 0 8
+$EndMeshFormat
+$PhysicalNames
+3
+1 0 "inlet"
+1 4 "obstacle"
+2 10 "fluid"
+$EndPhysicalNames
+$Nodes
+6
+1 0 0 0
+2 1 0 0
+3 1 1 0
+4 0 1 0
+5 0.5 0.5 0
+6 7 7 7
+$EndNodes
+$Elements
+9
+1 15 2 0 1 1
+2 15 2 0 2 2
+3 1 2 0 1 4 1
+4 1 2 4 2 1 2
+5 1 2 4 2 2 3
+6 2 2 10 1 1 2 5
+7 2 2 10 1 2 3 5
+8 2 2 10 1 3 4 5
+9 2 2 10 1 1 5 4
+$EndElements
+"""
+    p = tmp_path / "v22.msh"
+    p.write_text(txt)
+    m = pkg.Problem.read_msh(str(p), 2)
+    s = m.sizes()
+    assert (s["n_verts"], s["n_cells"], s["n_bfaces"]) == (5, 4, 3)  # node 6 is unused, points are skipped
+    assert sorted(m.array("bids").tolist()) == [0, 4, 4]
+    xyz, cells = m.array("xyz").reshape(-1, 2), m.array("cells").reshape(-1, 3)
+    area = np.linalg.det(xyz[cells[:, 1:]] - xyz[cells[:, :1]]) / 2
+    assert (area > 0).all() and abs(area.sum() - 1.0) < 1e-15  # the clockwise cell (1 5 4) was re-oriented
+    m.build(inlet=(pkg.INLET_PARABOLIC, 0.3, 1.0, 0))
+    assert m.sizes()["n_nodes"] == 5 + 8 and m.sizes()["n_p"] == 5  # vertices + edges
