@@ -199,6 +199,16 @@ int nsb_amg_coarsen_host_check(int64_t n, const int64_t *rowptr, const uint32_t 
                                int max_agg, int measure, const int32_t *owner, uint32_t *agg_out, int64_t *n_coarse_out,
                                int64_t *coarse_nnz_out);
 
+/* Host-only: the reference-cell contraction tables the assembly kernel works from (csrc/fe_tables.h), in the
+ * local dof order of deal.II's FE_SimplexP(2) / FE_SimplexP(1) (vertices, then lines (0,1),(1,2),(2,0)[,(0,3),(1,3),(2,3)]):
+ *   mhat[a*nn+b]                 = int phi_a phi_b
+ *   khat[(d*dim+e)*nn*nn + a*nn+b] = int d_d(phi_a) d_e(phi_b)
+ *   chat[(n*dim+d)*nn*nn + a*nn+b] = int phi_a phi_n d_d(phi_b)
+ *   dhat[(a*nv+k)*dim + d]        = int d_d(phi_a) psi_k
+ * over the reference simplex, evaluated with quadrature rule `rule` (NSB_QUAD_*).  nn = 6 / 10, nv = dim + 1.
+ * No device is touched. */
+int nsb_fe_tables_host_check(int dim, int rule, double *mhat, double *khat, double *chat, double *dhat);
+
 /* pinned host memory for callers that want asynchronous copies */
 void *nsb_alloc_pinned(int64_t bytes);
 void nsb_free_pinned(void *p);

@@ -2457,6 +2457,23 @@ int nsb_amg_coarsen_host_check(int64_t n, const int64_t *rowptr, const uint32_t 
   }
 }
 
+int nsb_fe_tables_host_check(int dim, int rule, double *mhat, double *khat, double *chat, double *dhat) {
+  if ((dim != 2 && dim != 3) || !mhat || !khat || !chat || !dhat) return NSB_EARG;
+  auto T = std::make_unique<FeTables>();
+  if (!fill_fe_tables(dim, rule, *T)) return NSB_EARG;
+  const int nn = T->nn, nv = T->nv;
+  for (int a = 0; a < nn; ++a)
+    for (int b = 0; b < nn; ++b) mhat[a * nn + b] = T->mhat[a][b];
+  for (int de = 0; de < dim * dim; ++de)
+    for (int p = 0; p < nn * nn; ++p) khat[(size_t)de * nn * nn + p] = T->khat[de][p];
+  for (int nd = 0; nd < nn * dim; ++nd)
+    for (int p = 0; p < nn * nn; ++p) chat[(size_t)nd * nn * nn + p] = T->chat[nd][p];
+  for (int a = 0; a < nn; ++a)
+    for (int k = 0; k < nv; ++k)
+      for (int d = 0; d < dim; ++d) dhat[((size_t)a * nv + k) * dim + d] = T->dhat[a][k][d];
+  return NSB_OK;
+}
+
 void *nsb_alloc_pinned(int64_t bytes) {
   void *p = nullptr;
   if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) {

@@ -23,7 +23,7 @@ SYMBOLS = [
     "nsb_bench_kernel", "nsb_launch_count", "nsb_timers", "nsb_info", "nsb_alloc_pinned", "nsb_free_pinned",
     "nsb_comm_unique_id", "nsb_comm_init", "nsb_set_local_dofs", "nsb_set_halo", "nsb_set_schur_solver", "nsb_gather_velocity",
     "nsb_slab_host_check", "nsb_gslab_host_check", "nsb_get_lumped_mass_inv",
-    "nsb_timer_start", "nsb_timer_stop", "nsb_cheb_coeffs_host_check", "nsb_skew_radius_host_check", "nsb_inner_params", "nsb_set_schur_strength", "nsb_amg_coarsen_host_check",
+    "nsb_timer_start", "nsb_timer_stop", "nsb_cheb_coeffs_host_check", "nsb_skew_radius_host_check", "nsb_inner_params", "nsb_set_schur_strength", "nsb_amg_coarsen_host_check", "nsb_fe_tables_host_check",
 ]
 
 
@@ -141,6 +141,21 @@ def skew_radius(H):
     if rc != 0:
         raise DeviceError(f"nsb_skew_radius_host_check failed ({rc})")
     return sig.value, y
+
+
+def fe_tables(dim, rule=QUAD_DEALII95):
+    """Reference-cell contraction tables of the assembly kernel (host only): dict mhat [nn,nn], khat [dim,dim,nn,nn],
+    chat [nn,dim,nn,nn] (chat[n,d,a,b] = int phi_a phi_n d_d phi_b), dhat [nn,nv,dim]."""
+    nn, nv = (6, 3) if dim == 2 else (10, 4)
+    L = device_lib()
+    dp = C.POINTER(C.c_double)
+    L.nsb_fe_tables_host_check.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp]
+    m, k, ch, dh = np.zeros(nn * nn), np.zeros(dim * dim * nn * nn), np.zeros(nn * dim * nn * nn), np.zeros(nn * nv * dim)
+    rc = L.nsb_fe_tables_host_check(dim, rule, _p(m, C.c_double), _p(k, C.c_double), _p(ch, C.c_double), _p(dh, C.c_double))
+    if rc != 0:
+        raise DeviceError(f"nsb_fe_tables_host_check failed ({rc})")
+    return {"mhat": m.reshape(nn, nn), "khat": k.reshape(dim, dim, nn, nn), "chat": ch.reshape(nn, dim, nn, nn),
+            "dhat": dh.reshape(nn, nv, dim)}
 
 
 def amg_coarsen(rowptr, colind, val, theta, max_agg=8, measure=0, owner=None):
